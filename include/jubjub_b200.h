@@ -1,0 +1,179 @@
+/*
+ * jubjub_b200.h -- C ABI of the B200-native batched Jubjub engine (libjubjub_b200.so).
+ *
+ * The reference (zkcrypto/jubjub 0.10.0) is a leaf Rust library with no FFI of its own; the
+ * boundary below is what a Rust shim's `extern "C"` block binds to add batch entry points
+ * (`batch_mul`, `batch_add`, `Fq::batch_mul`, ...) behind the unchanged jubjub:: types
+ * (INTEGRATION.md shows that shim).  Each entry point names the reference item it replaces
+ * (paths relative to /root/reference).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Data layout (all little-endian):
+ *   field element     32 B = 4 x u64 limbs.  Default: the reference's internal Montgomery
+ *                     form, i.e. what `Fr(pub(crate) [u64; 4])` (src/fr.rs:23) / bls12_381::Scalar
+ *                     hold.  With JJ_CANON: canonical integers < m, i.e. `to_bytes()` form
+ *                     (src/fr.rs:296-308); canonical inputs >= m are rejected per element.
+ *   ExtendedPoint     160 B = (u, v, z, t1, t2)            src/lib.rs:139-145
+ *   AffinePoint        64 B = (u, v)                       src/lib.rs:81-84
+ *   ExtendedNielsPoint 128 B = (v+u, v-u, z, t2d)          src/lib.rs:327-332
+ *   AffineNielsPoint   96 B = (v+u, v-u, t2d)              src/lib.rs:255-259
+ *   scalar             32 B canonical LE; bits 252..255 are ignored exactly as
+ *                      `multiply_bits` does (src/lib.rs:381-385).  With JJ_SCALAR_MONT the 32 B
+ *                      are Fr Montgomery limbs and are converted on the device (Fr::to_bytes,
+ *                      src/fr.rs:296-308, as `Mul<&Fr>` does at src/lib.rs:877).
+ *
+ * Inputs must satisfy the reference's type invariants (field elements < m, z != 0).
+ * Buffers are caller-owned and never retained.  Pointers are host memory unless
+ * JJ_DEVICE_PTRS is set (then: memory of ctx's device, 32-byte aligned).  `out` may alias
+ * an input of the same shape (the reference's `*Assign` operators, src/util.rs:126-152).
+ * Calls are synchronous unless JJ_ASYNC is set together with JJ_DEVICE_PTRS; then they are
+ * ordered on the context's stream and jj_sync() waits for them.
+ * A context is not thread-safe; use one per thread or per GPU.
+ *
+ * Every function returns JJ_OK (0) or a negative error; nothing throws or aborts.
+ * Per-element failures that the reference reports as CtOption::none (invert of zero,
+ * src/fr.rs:539; non-canonical bytes, src/fr.rs:291; off-curve encodings, src/lib.rs:492-534)
+ * are reported in a `uint8_t ok[n]` side array, not as an error.
+ *
+ * The batch entry points are variable-time in their data; the reference's constant-time
+ * policy (src/lib.rs:12-17) is kept by its scalar API, not by this batch engine.
+ */
+#ifndef JUBJUB_B200_H
+#define JUBJUB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jj_ctx jj_ctx;
+
+enum {
+    JJ_OK = 0,
+    JJ_ERR_INVALID_ARG = -1, /* null pointer, misaligned device pointer, bad flag, length mismatch
+                                (the reference panics: assert_eq! at src/lib.rs:841) */
+    JJ_ERR_CUDA = -2,
+    JJ_ERR_NCCL = -3,
+    JJ_ERR_OOM = -4,
+    JJ_ERR_NO_DEVICE = -5
+};
+
+enum {
+    JJ_MONT = 0u,          /* field elements are Montgomery limbs (default)                   */
+    JJ_CANON = 1u << 0,    /* field elements (in and out) are canonical integers             */
+    JJ_DEVICE_PTRS = 1u << 1,
+    JJ_ASYNC = 1u << 2,
+    JJ_SUBTRACT = 1u << 3, /* point add entry points compute p - q (src/lib.rs:922-940, 970-988, 1001-1008) */
+    JJ_SCALAR_MONT = 1u << 4,
+    JJ_OUT_AFFINE = 1u << 5, /* scalar-mul writes normalised AffinePoint (64 B) instead of Extended */
+    JJ_OUT_BYTES = 1u << 6   /* scalar-mul writes the 32-byte encoding (src/lib.rs:455-464)      */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int32_t jj_init(int device, jj_ctx** out);
+int32_t jj_destroy(jj_ctx* ctx);
+int32_t jj_sync(jj_ctx* ctx);
+const char* jj_last_error(const jj_ctx* ctx);
+const char* jj_version(void);
+int32_t jj_device_info(jj_ctx* ctx, int32_t* sm_count, int32_t* sm_clock_khz, uint64_t* hbm_bytes);
+/* Tuning knob for the variable-base kernel variant; 0 = library default. */
+int32_t jj_set_scalar_mul_variant(jj_ctx* ctx, int32_t variant);
+/* Number of this library's kernel launches issued on ctx so far (bench.py's gpu_launches). */
+uint64_t jj_launch_count(const jj_ctx* ctx);
+
+/* Device/pinned memory and a device timer, so hosts without a CUDA binding can keep
+ * batches resident and time them on the context's stream with CUDA events. */
+int32_t jj_malloc(jj_ctx* ctx, size_t bytes, void** dptr);
+int32_t jj_free(jj_ctx* ctx, void* dptr);
+int32_t jj_host_alloc(jj_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int32_t jj_host_free(jj_ctx* ctx, void* hptr);
+int32_t jj_memcpy_h2d(jj_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
+int32_t jj_memcpy_d2h(jj_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
+int32_t jj_timer_start(jj_ctx* ctx);
+int32_t jj_timer_stop(jj_ctx* ctx, float* elapsed_ms);
+int32_t jj_flush_l2(jj_ctx* ctx); /* overwrites a scratch buffer larger than L2 */
+/* Measures the chip's IMAD.WIDE.U32 issue rate (instructions x 32 lanes per second) with a
+ * register-only kernel: the integer-pipe roofline denominator. */
+int32_t jj_measure_imad_peak(jj_ctx* ctx, double* imad_per_sec);
+
+/* ---- field batches: out[i] = a[i] (op) b[i]; field = Fq (jj_fq_*) or Fr (jj_fr_*) --------- */
+/* Fr::mul src/fr.rs:592-616 (+ montgomery_reduce :544-588); Fq = [ext] bls12_381::Scalar, same shape */
+int32_t jj_fq_mul(jj_ctx* ctx, const void* a, const void* b, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_mul(jj_ctx* ctx, const void* a, const void* b, void* out, size_t n, uint32_t flags);
+/* Fr::square src/fr.rs:353-381 */
+int32_t jj_fq_square(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_square(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t flags);
+/* Fr::add src/fr.rs:638-647, Fr::sub :620-634, Fr::neg :651-665, Fr::double :261-263 */
+int32_t jj_fq_add(jj_ctx* ctx, const void* a, const void* b, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_add(jj_ctx* ctx, const void* a, const void* b, void* out, size_t n, uint32_t flags);
+int32_t jj_fq_sub(jj_ctx* ctx, const void* a, const void* b, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_sub(jj_ctx* ctx, const void* a, const void* b, void* out, size_t n, uint32_t flags);
+int32_t jj_fq_neg(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_neg(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t flags);
+int32_t jj_fq_double(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_double(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t flags);
+/* Fr::invert src/fr.rs:438-540; ok[i] = 0 and out[i] = 0 for a[i] = 0 (CtOption::none) */
+int32_t jj_fq_invert(jj_ctx* ctx, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags);
+int32_t jj_fr_invert(jj_ctx* ctx, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags);
+/* Fr::to_bytes src/fr.rs:296-308: Montgomery limbs -> 32 canonical LE bytes */
+int32_t jj_fq_to_bytes(jj_ctx* ctx, const void* a, void* out32, size_t n, uint32_t flags);
+int32_t jj_fr_to_bytes(jj_ctx* ctx, const void* a, void* out32, size_t n, uint32_t flags);
+/* Fr::from_bytes src/fr.rs:268-292: ok[i] = 0 when the 32 bytes are >= m */
+int32_t jj_fq_from_bytes(jj_ctx* ctx, const void* in32, void* out, uint8_t* ok, size_t n, uint32_t flags);
+int32_t jj_fr_from_bytes(jj_ctx* ctx, const void* in32, void* out, uint8_t* ok, size_t n, uint32_t flags);
+/* Fr::from_bytes_wide src/fr.rs:312-343: 64 LE bytes -> d0*R2 + d1*R3 */
+int32_t jj_fq_from_bytes_wide(jj_ctx* ctx, const void* in64, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_from_bytes_wide(jj_ctx* ctx, const void* in64, void* out, size_t n, uint32_t flags);
+/* Synthetic inputs: element i = from_bytes_wide(SplitMix64(seed) outputs [8(first+i), 8(first+i)+8)). */
+int32_t jj_fq_stream(jj_ctx* ctx, uint64_t seed, size_t first, void* out, size_t n, uint32_t flags);
+int32_t jj_fr_stream(jj_ctx* ctx, uint64_t seed, size_t first, void* out, size_t n, uint32_t flags);
+
+/* ---- point batches (ExtendedPoint in, ExtendedPoint out; formulas verbatim => 160 B bit-exact) */
+/* ExtendedPoint::double src/lib.rs:739-828 */
+int32_t jj_point_double(jj_ctx* ctx, const void* p_ext, void* out_ext, size_t n, uint32_t flags);
+/* &ExtendedPoint + &ExtendedPoint src/lib.rs:992-1008 (to_niels :728-735, then the 8M add :883-940) */
+int32_t jj_point_add(jj_ctx* ctx, const void* p_ext, const void* q_ext, void* out_ext, size_t n, uint32_t flags);
+/* &ExtendedPoint + &ExtendedNielsPoint src/lib.rs:883-940 */
+int32_t jj_point_add_niels(jj_ctx* ctx, const void* p_ext, const void* q_niels, void* out_ext, size_t n, uint32_t flags);
+/* &ExtendedPoint + &AffineNielsPoint src/lib.rs:944-988 */
+int32_t jj_point_add_affine_niels(jj_ctx* ctx, const void* p_ext, const void* q_aniels, void* out_ext, size_t n, uint32_t flags);
+/* ExtendedPoint::to_niels src/lib.rs:728-735; AffinePoint::to_niels :652-658 */
+int32_t jj_point_to_niels(jj_ctx* ctx, const void* p_ext, void* out_niels, size_t n, uint32_t flags);
+int32_t jj_affine_to_niels(jj_ctx* ctx, const void* p_affine, void* out_aniels, size_t n, uint32_t flags);
+
+/* out[i] = [scalars[i]] points[i]: `&ExtendedPoint * &Fr` src/lib.rs:873-879 ->
+ * ExtendedPoint::multiply :830-833 -> ExtendedNielsPoint::multiply :356-379.
+ * Output: ExtendedPoint (projectively equal to the reference's, affine-identical), or with
+ * JJ_OUT_AFFINE / JJ_OUT_BYTES the normalised point / its encoding (bit-exact). */
+int32_t jj_scalar_mul(jj_ctx* ctx, const void* points_ext, const void* scalars32, void* out, size_t n, uint32_t flags);
+/* out[i] = [scalars[i]] base: `&AffinePoint * &Fr` src/lib.rs:1109-1115 -> AffineNielsPoint::multiply :271-295,
+ * one shared base; the per-window AffineNiels table is built once per base and cached in ctx. */
+int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* scalars32, void* out, size_t n, uint32_t flags);
+/* batch_normalize src/lib.rs:840-858 / :1084-1107: ExtendedPoint -> AffinePoint (z = 0 gives (0, 0)
+ * like ff::BatchInverter's skipped zeros) */
+int32_t jj_batch_normalize(jj_ctx* ctx, const void* in_ext, void* out_affine, size_t n, uint32_t flags);
+/* AffinePoint::to_bytes src/lib.rs:455-464 */
+int32_t jj_affine_to_bytes(jj_ctx* ctx, const void* in_affine, void* out32, size_t n, uint32_t flags);
+/* ExtendedPoint::is_torsion_free src/lib.rs:709-711 ([r]P == identity), is_identity :691-696,
+ * is_small_order :699-705; flags_out[i] in {0, 1} */
+int32_t jj_is_torsion_free(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
+int32_t jj_is_identity(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
+int32_t jj_is_small_order(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
+
+/* ---- multi-GPU: one context (one process) per GPU, contiguous block partition of the batch --- */
+/* rank g of G owns units [g*n/G, (g+1)*n/G).  jj_comm_unique_id fills a 128-byte NCCL id on one
+ * rank; the host distributes it (torch.distributed / MPI / files) and every rank calls jj_comm_init. */
+int32_t jj_comm_unique_id(void* id128);
+int32_t jj_comm_init(jj_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int32_t jj_comm_destroy(jj_ctx* ctx);
+/* Computes this rank's shard of out = [scalars] points (shard-local device inputs of n_local units)
+ * and all-gathers the results: out_all (device, nranks * n_local units) holds every rank's outputs
+ * in rank order.  Output unit = ExtendedPoint, or per JJ_OUT_AFFINE / JJ_OUT_BYTES. */
+int32_t jj_scalar_mul_sharded(jj_ctx* ctx, const void* points_ext_local, const void* scalars32_local,
+                              void* out_all, size_t n_local, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

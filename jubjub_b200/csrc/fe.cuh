@@ -1,0 +1,392 @@
+// fe.cuh -- 256-bit Montgomery field arithmetic for Jubjub's Fq and Fr on sm_100a.
+//
+// A field element is 8 x u32 little-endian limbs held in registers; in memory it is
+// byte-identical to the reference's 4 x u64 Montgomery limbs (src/fr.rs:23, R = 2^256).
+// Every operation returns the fully reduced representative in [0, m), so results are
+// the same bits the reference produces (uniqueness argument).
+//
+// What replaces what (paths relative to /root/reference):
+//   mont_mul    <- Fr::mul + montgomery_reduce   src/fr.rs:592-616, 544-588  ([ext] Fq same shape)
+//   mont_sqr    <- Fr::square                    src/fr.rs:353-381
+//   fe_add/sub/neg/dbl <- Fr::add/sub/neg/double src/fr.rs:638-647, 620-634, 651-665, 261-263
+//   fe_to_canonical    <- Fr::to_bytes           src/fr.rs:296-308
+//   fe_invert          <- Fr::invert / [ext] Fq::invert   src/fr.rs:438-540
+//
+// Multiplication is an operand-scanning (CIOS) Montgomery product on 32-bit limbs with
+// the even/odd column split: products whose column index is even accumulate into one
+// 8-word array, odd ones into another that sits one word higher, so every row is two
+// independent carry chains of four IMAD.WIDE.U32 each and no chain ever has to
+// propagate a carry across the other's words.  Per product: 64 IMAD.WIDE (a*b) +
+// 64 IMAD.WIDE (q*m) + 8 IMAD (q) = 136 integer-pipe instructions; everything else
+// (merges, conditional subtract) is IADD3/LOP3/SEL work on the other pipe.
+//
+// Precondition shared with the reference's type invariant: the first operand `a` of
+// mont_mul is canonical (< m).  The second operand may be any 256-bit value (this is
+// what from_raw / from_bytes rely on, src/fr.rs:347-349).
+#pragma once
+#include "ptx_ops.cuh"
+
+namespace jj {
+
+struct fe {
+    uint32_t w[8];
+};
+
+// ---- field parameters (32-bit limbs of the constants in SURVEY.md section 8a) ------
+struct FqP {  // [ext] bls12_381::Scalar modulus q; q-1 is at src/lib.rs:1629-1634
+    static constexpr uint32_t M0 = 0x00000001u, M1 = 0xffffffffu, M2 = 0xfffe5bfeu, M3 = 0x53bda402u,
+                              M4 = 0x09a1d805u, M5 = 0x3339d808u, M6 = 0x299d7d48u, M7 = 0x73eda753u;
+    static constexpr uint32_t INV = 0xffffffffu;  // -q^-1 mod 2^32
+    // R = 2^256 mod q, R2 = 2^512 mod q, R3 = 2^768 mod q
+    JJ_CONST_FN uint32_t R(int i) {
+        constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t R3(int i) {
+        constexpr uint32_t t[8] = {0x439b73afu, 0xc62c1807u, 0x8cf06990u, 0x1b3e0d18u, 0xc7b5f418u, 0x73d13c71u, 0xc8db33e9u, 0x6e2a5bb9u};
+        return t[i];
+    }
+    // m - 2, the Fermat inversion exponent
+    JJ_CONST_FN uint32_t M_MINUS_2(int i) {
+        constexpr uint32_t t[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return t[i];
+    }
+};
+struct FrP {  // src/fr.rs:77-82 (MODULUS), :214 (INV), :217-238 (R, R2, R3)
+    static constexpr uint32_t M0 = 0xd6f72cb7u, M1 = 0xd0970e5eu, M2 = 0xccc81082u, M3 = 0xa6682093u,
+                              M4 = 0x01343b00u, M5 = 0x06673b01u, M6 = 0x6533afa9u, M7 = 0x0e7db4eau;
+    static constexpr uint32_t INV = 0xef788ef9u;
+    JJ_CONST_FN uint32_t R(int i) {
+        constexpr uint32_t t[8] = {0xb99607d9u, 0x25f80bb3u, 0x66b6e750u, 0xf315d62fu, 0xeb8814f4u, 0x932514eeu, 0x479155c6u, 0x09a6fc6fu};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0x95e57731u, 0x67719aa4u, 0x9ce3fc26u, 0x51b0cef0u, 0xc026e9a5u, 0x69dab7fau, 0x8d127688u, 0x04f6547bu};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t R3(int i) {
+        constexpr uint32_t t[8] = {0x3d830544u, 0xe0d6c656u, 0x598d0f85u, 0x323e3883u, 0x4c2e2ba8u, 0xf0fea300u, 0x946737ecu, 0x05874f84u};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t M_MINUS_2(int i) {
+        constexpr uint32_t t[8] = {0xd6f72cb5u, 0xd0970e5eu, 0xccc81082u, 0xa6682093u, 0x01343b00u, 0x06673b01u, 0x6533afa9u, 0x0e7db4eau};
+        return t[i];
+    }
+};
+
+// word i of m - 2 with a run-time index (constexpr arrays cannot be ODR-used on the device)
+template <class F>
+JJ_DEVICE uint32_t exp_word_m_minus_2(int i) {
+    switch (i) {
+        case 0: return F::M_MINUS_2(0); case 1: return F::M_MINUS_2(1);
+        case 2: return F::M_MINUS_2(2); case 3: return F::M_MINUS_2(3);
+        case 4: return F::M_MINUS_2(4); case 5: return F::M_MINUS_2(5);
+        case 6: return F::M_MINUS_2(6); default: return F::M_MINUS_2(7);
+    }
+}
+
+// ---- small helpers ---------------------------------------------------------------
+JJ_DEVICE void fe_set_zero(fe& r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = 0;
+}
+template <class F>
+JJ_DEVICE void fe_set_one(fe& r) {  // Montgomery one = R
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = F::R(i);
+}
+JJ_DEVICE bool fe_is_zero(const fe& a) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t |= a.w[i];
+    return t == 0;
+}
+JJ_DEVICE bool fe_eq(const fe& a, const fe& b) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t |= a.w[i] ^ b.w[i];
+    return t == 0;
+}
+// r = c ? b : a   (the reference's conditional_select, src/fr.rs:66-75)
+JJ_DEVICE void fe_select(fe& r, const fe& a, const fe& b, bool c) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = c ? b.w[i] : a.w[i];
+}
+JJ_DEVICE void fe_cswap(fe& a, fe& b, bool c) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t x = a.w[i], y = b.w[i];
+        a.w[i] = c ? y : x;
+        b.w[i] = c ? x : y;
+    }
+}
+
+// r in [0, 2m)  ->  [0, m): trial-subtract m, keep the difference unless it borrowed.
+// Same value as the reference's sub(&MODULUS) with mask add-back (src/fr.rs:587, 620-634).
+template <class F>
+JJ_DEVICE void fe_reduce_once(uint32_t r[8]) {
+    uint32_t d[8], borrow;
+    JJ_SUB_CC_I(d[0], r[0], F::M0);
+    JJ_SUBC_CC_I(d[1], r[1], F::M1);
+    JJ_SUBC_CC_I(d[2], r[2], F::M2);
+    JJ_SUBC_CC_I(d[3], r[3], F::M3);
+    JJ_SUBC_CC_I(d[4], r[4], F::M4);
+    JJ_SUBC_CC_I(d[5], r[5], F::M5);
+    JJ_SUBC_CC_I(d[6], r[6], F::M6);
+    JJ_SUBC_CC_I(d[7], r[7], F::M7);
+    subc(borrow, 0u, 0u);  // 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : d[i];
+}
+
+// ---- add / sub / neg / double ------------------------------------------------------
+template <class F>
+JJ_DEVICE void fe_add(fe& r, const fe& a, const fe& b) {
+    uint32_t s[8];
+    add_cc(s[0], a.w[0], b.w[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(s[i], a.w[i], b.w[i]);
+    addc(s[7], a.w[7], b.w[7]);  // 2m < 2^256: no carry out
+    fe_reduce_once<F>(s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = s[i];
+}
+template <class F>
+JJ_DEVICE void fe_dbl(fe& r, const fe& a) {
+    fe_add<F>(r, a, a);
+}
+template <class F>
+JJ_DEVICE void fe_sub(fe& r, const fe& a, const fe& b) {
+    uint32_t d[8], mask;
+    sub_cc(d[0], a.w[0], b.w[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) subc_cc(d[i], a.w[i], b.w[i]);
+    subc(mask, 0u, 0u);  // all-ones when a < b
+    add_cc(d[0], d[0], F::M0 & mask);
+    addc_cc(d[1], d[1], F::M1 & mask);
+    addc_cc(d[2], d[2], F::M2 & mask);
+    addc_cc(d[3], d[3], F::M3 & mask);
+    addc_cc(d[4], d[4], F::M4 & mask);
+    addc_cc(d[5], d[5], F::M5 & mask);
+    addc_cc(d[6], d[6], F::M6 & mask);
+    addc(d[7], d[7], F::M7 & mask);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = d[i];
+}
+template <class F>
+JJ_DEVICE void fe_neg(fe& r, const fe& a) {
+    uint32_t d[8], nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nz |= a.w[i];
+    uint32_t mask = nz ? 0xffffffffu : 0u;  // -0 = 0 (src/fr.rs:661-664)
+    sub_cc(d[0], F::M0, a.w[0]);
+    subc_cc(d[1], F::M1, a.w[1]);
+    subc_cc(d[2], F::M2, a.w[2]);
+    subc_cc(d[3], F::M3, a.w[3]);
+    subc_cc(d[4], F::M4, a.w[4]);
+    subc_cc(d[5], F::M5, a.w[5]);
+    subc_cc(d[6], F::M6, a.w[6]);
+    subc(d[7], F::M7, a.w[7]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = d[i] & mask;
+}
+
+// ---- Montgomery multiplication -------------------------------------------------------
+// One reduction row: q = E[0] * (-m^-1); E += q*(m0,m2,m4,m6); O += q*(m1,m3,m5,m7).
+// E is the array whose word 0 sits at the current column, O sits one column higher.
+// After the row E[0] == 0.  The O chain cannot carry out (running total < 2^(32*9) at
+// this column, see DESIGN.md "carry bounds"); the E chain's carry lands in O[7].
+template <class F>
+JJ_DEVICE void redc_row(uint32_t E[8], uint32_t O[8]) {
+    uint32_t q = E[0] * F::INV;
+    JJ_MAD_LO_CC_I(O[0], q, F::M1, O[0]);
+    JJ_MADC_HI_CC_I(O[1], q, F::M1, O[1]);
+    JJ_MADC_LO_CC_I(O[2], q, F::M3, O[2]);
+    JJ_MADC_HI_CC_I(O[3], q, F::M3, O[3]);
+    JJ_MADC_LO_CC_I(O[4], q, F::M5, O[4]);
+    JJ_MADC_HI_CC_I(O[5], q, F::M5, O[5]);
+    JJ_MADC_LO_CC_I(O[6], q, F::M7, O[6]);
+    JJ_MADC_HI_I(O[7], q, F::M7, O[7]);
+    JJ_MAD_LO_CC_I(E[0], q, F::M0, E[0]);
+    JJ_MADC_HI_CC_I(E[1], q, F::M0, E[1]);
+    JJ_MADC_LO_CC_I(E[2], q, F::M2, E[2]);
+    JJ_MADC_HI_CC_I(E[3], q, F::M2, E[3]);
+    JJ_MADC_LO_CC_I(E[4], q, F::M4, E[4]);
+    JJ_MADC_HI_CC_I(E[5], q, F::M4, E[5]);
+    JJ_MADC_LO_CC_I(E[6], q, F::M6, E[6]);
+    JJ_MADC_HI_CC_I(E[7], q, F::M6, E[7]);
+    addc(O[7], O[7], 0u);
+}
+// Fq specialisation.  q's low limbs are m0 = 1, m1 = 2^32 - 1 and -q^-1 = 2^32 - 1, so
+//   k       = -E[0]                                   (no multiply)
+//   k * m0  : column 0 cancels E[0]; its carry c0 = [E[0] != 0] moves one column up
+//   k * m1  = k * 2^32 - k : low word = E[0], high word = k - c0
+// i.e. O[0] += E[0] + c0 and O[1] += k - c0, all IADD3 work on the ALU pipe.  That
+// removes 3 of the 17 integer-multiplier instructions of every row (136 -> 112 per
+// product) and leaves E[1] untouched.
+template <>
+JJ_DEVICE_SPEC void redc_row<FqP>(uint32_t E[8], uint32_t O[8]) {
+    uint32_t e0 = E[0], q, hi, t;
+    sub_cc(q, 0u, e0);   // q = -e0, borrow = c0
+    subc(hi, q, 0u);     // hi = q - c0
+    add_cc(t, e0, 0xffffffffu);  // carry = c0
+    addc_cc(O[0], O[0], e0);
+    addc_cc(O[1], O[1], hi);
+    JJ_MADC_LO_CC_I(O[2], q, FqP::M3, O[2]);
+    JJ_MADC_HI_CC_I(O[3], q, FqP::M3, O[3]);
+    JJ_MADC_LO_CC_I(O[4], q, FqP::M5, O[4]);
+    JJ_MADC_HI_CC_I(O[5], q, FqP::M5, O[5]);
+    JJ_MADC_LO_CC_I(O[6], q, FqP::M7, O[6]);
+    JJ_MADC_HI_I(O[7], q, FqP::M7, O[7]);
+    JJ_MAD_LO_CC_I(E[2], q, FqP::M2, E[2]);
+    JJ_MADC_HI_CC_I(E[3], q, FqP::M2, E[3]);
+    JJ_MADC_LO_CC_I(E[4], q, FqP::M4, E[4]);
+    JJ_MADC_HI_CC_I(E[5], q, FqP::M4, E[5]);
+    JJ_MADC_LO_CC_I(E[6], q, FqP::M6, E[6]);
+    JJ_MADC_HI_CC_I(E[7], q, FqP::M6, E[7]);
+    addc(O[7], O[7], 0u);
+    E[0] = 0;
+    (void)t;
+}
+// One product row for multiplier word bi.  On entry O is the array that was column-
+// aligned in the previous row: O[0] is dead (zeroed by redc_row), O[1] sits at this
+// row's column and is folded into E[0]; O[2..7] slide down two words while the odd
+// products are added, so O ends up one column above E again.
+JJ_DEVICE void mul_row(uint32_t E[8], uint32_t O[8], const uint32_t a[8], uint32_t bi) {
+    add_cc(E[0], E[0], O[1]);
+    madc_lo_cc(O[0], a[1], bi, O[2]);
+    madc_hi_cc(O[1], a[1], bi, O[3]);
+    madc_lo_cc(O[2], a[3], bi, O[4]);
+    madc_hi_cc(O[3], a[3], bi, O[5]);
+    madc_lo_cc(O[4], a[5], bi, O[6]);
+    madc_hi_cc(O[5], a[5], bi, O[7]);
+    madc_lo_cc(O[6], a[7], bi, 0u);
+    madc_hi(O[7], a[7], bi, 0u);
+    mad_lo_cc(E[0], a[0], bi, E[0]);
+    madc_hi_cc(E[1], a[0], bi, E[1]);
+    madc_lo_cc(E[2], a[2], bi, E[2]);
+    madc_hi_cc(E[3], a[2], bi, E[3]);
+    madc_lo_cc(E[4], a[4], bi, E[4]);
+    madc_hi_cc(E[5], a[4], bi, E[5]);
+    madc_lo_cc(E[6], a[6], bi, E[6]);
+    madc_hi_cc(E[7], a[6], bi, E[7]);
+    addc(O[7], O[7], 0u);
+}
+// First row: nothing accumulated yet, plain 32x32->64 products (IMAD.WIDE.U32 with RZ).
+JJ_DEVICE void mul_row0(uint32_t E[8], uint32_t O[8], const uint32_t a[8], uint32_t b0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint64_t e = (uint64_t)a[2 * k] * b0, o = (uint64_t)a[2 * k + 1] * b0;
+        E[2 * k] = (uint32_t)e;
+        E[2 * k + 1] = (uint32_t)(e >> 32);
+        O[2 * k] = (uint32_t)o;
+        O[2 * k + 1] = (uint32_t)(o >> 32);
+    }
+}
+// After the last row: E holds columns 8..14 in E[1..7] (E[0] dead), O holds 8..15.
+template <class F>
+JJ_DEVICE void mont_finish(fe& r, const uint32_t E[8], const uint32_t O[8]) {
+    uint32_t s[8];
+    add_cc(s[0], O[0], E[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(s[i], O[i], E[i + 1]);
+    addc(s[7], O[7], 0u);
+    fe_reduce_once<F>(s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = s[i];
+}
+
+// r = a * b * 2^-256 mod m.  `a` canonical, `b` any 256-bit value.  r may alias a or b.
+template <class F>
+JJ_DEVICE void mont_mul(fe& r, const fe& a, const fe& b) {
+    uint32_t X[8], Y[8];
+    mul_row0(X, Y, a.w, b.w[0]);
+    redc_row<F>(X, Y);
+    mul_row(Y, X, a.w, b.w[1]);
+    redc_row<F>(Y, X);
+    mul_row(X, Y, a.w, b.w[2]);
+    redc_row<F>(X, Y);
+    mul_row(Y, X, a.w, b.w[3]);
+    redc_row<F>(Y, X);
+    mul_row(X, Y, a.w, b.w[4]);
+    redc_row<F>(X, Y);
+    mul_row(Y, X, a.w, b.w[5]);
+    redc_row<F>(Y, X);
+    mul_row(X, Y, a.w, b.w[6]);
+    redc_row<F>(X, Y);
+    mul_row(Y, X, a.w, b.w[7]);
+    redc_row<F>(Y, X);
+    mont_finish<F>(r, Y, X);
+}
+
+template <class F>
+JJ_DEVICE void mont_sqr(fe& r, const fe& a) {
+    mont_mul<F>(r, a, a);
+}
+
+// Montgomery form -> canonical integer: one reduction of (a, 0), i.e. a * 1 (src/fr.rs:296-308).
+template <class F>
+JJ_DEVICE void fe_to_canonical(fe& r, const fe& a) {
+    fe one;
+    fe_set_zero(one);
+    one.w[0] = 1;
+    mont_mul<F>(r, a, one);
+}
+// canonical (or any 256-bit) integer -> Montgomery form: R2 * v (src/fr.rs:347-349).
+template <class F>
+JJ_DEVICE void fe_from_raw(fe& r, const fe& v) {
+    fe r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.w[i] = F::R2(i);
+    mont_mul<F>(r, r2, v);
+}
+// v < m ?  (the canonical check of from_bytes, src/fr.rs:277-286)
+template <class F>
+JJ_DEVICE bool fe_is_canonical(const fe& v) {
+    uint32_t d, borrow;
+    JJ_SUB_CC_I(d, v.w[0], F::M0);
+    JJ_SUBC_CC_I(d, v.w[1], F::M1);
+    JJ_SUBC_CC_I(d, v.w[2], F::M2);
+    JJ_SUBC_CC_I(d, v.w[3], F::M3);
+    JJ_SUBC_CC_I(d, v.w[4], F::M4);
+    JJ_SUBC_CC_I(d, v.w[5], F::M5);
+    JJ_SUBC_CC_I(d, v.w[6], F::M6);
+    JJ_SUBC_CC_I(d, v.w[7], F::M7);
+    subc(borrow, 0u, 0u);
+    (void)d;
+    return borrow != 0;
+}
+
+// a^(m-2): 4-bit fixed-window exponentiation over the constant exponent.  The result is
+// the unique inverse (0 for a = 0, flagged by the caller like CtOption, src/fr.rs:539),
+// so the reference's particular addition chain (src/fr.rs:438-538) need not be replayed.
+template <class F>
+JJ_DEVICE void fe_invert(fe& r, const fe& a) {
+    fe tbl[16];
+    fe_set_one<F>(tbl[0]);
+    tbl[1] = a;
+#pragma unroll 1
+    for (int i = 2; i < 16; i++) mont_mul<F>(tbl[i], tbl[i - 1], a);
+    fe acc;
+    fe_set_one<F>(acc);
+#pragma unroll 1
+    for (int wi = 7; wi >= 0; wi--) {
+        uint32_t e = exp_word_m_minus_2<F>(wi);
+#pragma unroll 1
+        for (int s = 28; s >= 0; s -= 4) {
+            mont_sqr<F>(acc, acc);
+            mont_sqr<F>(acc, acc);
+            mont_sqr<F>(acc, acc);
+            mont_sqr<F>(acc, acc);
+            uint32_t d = (e >> s) & 15u;
+            mont_mul<F>(acc, acc, tbl[d]);
+        }
+    }
+    r = acc;
+}
+
+}  // namespace jj

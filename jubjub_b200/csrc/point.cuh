@@ -1,0 +1,172 @@
+// point.cuh -- Jubjub twisted-Edwards group law on register-resident field elements.
+//
+// Coordinate systems and formulas are the reference's, verbatim in *sequence* so that
+// point_add / point_double outputs are bit-identical 160-byte extended points
+// (SURVEY.md section 8c).  Paths relative to /root/reference:
+//   ext_point   (U, V, Z, T1, T2), T1*T2 = UV/Z        src/lib.rs:139-145
+//   ext_niels   (V+U, V-U, Z, T1*T2*2d)                src/lib.rs:327-332
+//   aff_niels   (v+u, v-u, u*v*2d)                     src/lib.rs:255-259
+//   point_double      4S + 3M                          src/lib.rs:739-828
+//   point_add_niels   8M  (sub: swapped halves)        src/lib.rs:883-940
+//   point_add_aff_niels 7M                             src/lib.rs:944-988
+//   into_extended     3M                               src/lib.rs:1052-1060
+//   to_niels          2M                               src/lib.rs:728-735, 652-658
+#pragma once
+#include "fe.cuh"
+
+namespace jj {
+
+struct aff_point { fe u, v; };
+struct ext_point { fe u, v, z, t1, t2; };
+struct ext_niels { fe vpu, vmu, z, t2d; };
+struct aff_niels { fe vpu, vmu, t2d; };
+
+// Montgomery-form curve constants: d = -(10240/10241) (src/lib.rs:399-404), 2d (:407-412),
+// generator (u, 11) (:1380-1396).  Values are from_raw(...) of the reference's raw limbs,
+// recomputed in oracle/model.py and checked in tests/test_oracle_kat.py.
+struct Curve {
+    JJ_CONST_FN uint32_t D(int i) {
+        constexpr uint32_t t[8] = {0xb974f6b0u, 0x2a522455u, 0x0d9acab3u, 0xfc6cc9efu, 0xc27628d1u, 0x7a08fb94u, 0xfe0e262eu, 0x57f8f6a8u};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t D2(int i) {
+        constexpr uint32_t t[8] = {0x72e9ed5fu, 0x54a448acu, 0x1b373967u, 0xa51befdbu, 0x7b4a799eu, 0xc0d81f21u, 0xd27ecf14u, 0x3c0445feu};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t GEN_U(int i) {
+        constexpr uint32_t t[8] = {0xc166eca5u, 0x50c87a58u, 0xc0051afcu, 0x8046fd74u, 0x695b0493u, 0x406355eeu, 0x1bdc7e0au, 0x0d5a8d93u};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t GEN_V(int i) {
+        constexpr uint32_t t[8] = {0xffffffe8u, 0x00000017u, 0x00276018u, 0x26389fb8u, 0x18d3bf80u, 0x3293bf3fu, 0x193c413bu, 0x21b85034u};
+        return t[i];
+    }
+};
+
+#define JJ_LOAD_CONST(r, ACCESSOR)                          \
+    do {                                                   \
+        _Pragma("unroll") for (int i_ = 0; i_ < 8; i_++)(r).w[i_] = ACCESSOR(i_); \
+    } while (0)
+
+JJ_DEVICE void point_set_identity(ext_point& p) {  // (0, 1, 1, 0, 0)  src/lib.rs:680-688
+    fe_set_zero(p.u);
+    fe_set_one<FqP>(p.v);
+    fe_set_one<FqP>(p.z);
+    fe_set_zero(p.t1);
+    fe_set_zero(p.t2);
+}
+JJ_DEVICE void point_from_affine(ext_point& p, const aff_point& a) {  // src/lib.rs:214-226
+    p.u = a.u;
+    p.v = a.v;
+    fe_set_one<FqP>(p.z);
+    p.t1 = a.u;
+    p.t2 = a.v;
+}
+JJ_DEVICE void point_neg(ext_point& r, const ext_point& p) {  // src/lib.rs:196-210
+    fe_neg<FqP>(r.u, p.u);
+    r.v = p.v;
+    r.z = p.z;
+    fe_neg<FqP>(r.t1, p.t1);
+    r.t2 = p.t2;
+}
+
+// completed point (u, v, z, t) -> extended (u*t, v*z, z*t, u, v)
+JJ_DEVICE void into_extended(ext_point& r, const fe& cu, const fe& cv, const fe& cz, const fe& ct) {
+    fe u, v, z;
+    mont_mul<FqP>(u, cu, ct);
+    mont_mul<FqP>(v, cv, cz);
+    mont_mul<FqP>(z, cz, ct);
+    r.t1 = cu;
+    r.t2 = cv;
+    r.u = u;
+    r.v = v;
+    r.z = z;
+}
+
+JJ_DEVICE void point_double(ext_point& r, const ext_point& p) {
+    fe uu, vv, zz2, uv2, vpu, vmu, cu, ct;
+    mont_sqr<FqP>(uu, p.u);
+    mont_sqr<FqP>(vv, p.v);
+    mont_sqr<FqP>(zz2, p.z);
+    fe_dbl<FqP>(zz2, zz2);
+    fe_add<FqP>(uv2, p.u, p.v);
+    mont_sqr<FqP>(uv2, uv2);
+    fe_add<FqP>(vpu, vv, uu);
+    fe_sub<FqP>(vmu, vv, uu);
+    fe_sub<FqP>(cu, uv2, vpu);
+    fe_sub<FqP>(ct, zz2, vmu);
+    into_extended(r, cu, vpu, vmu, ct);
+}
+
+// p + n (sub = false) or p - n (sub = true) for an extended-Niels operand.
+JJ_DEVICE void point_add_niels(ext_point& r, const ext_point& p, const ext_niels& n, bool sub) {
+    fe a, b, c, d, t, n1, n2;
+    fe_select(n1, n.vmu, n.vpu, sub);  // multiplies (v - u)
+    fe_select(n2, n.vpu, n.vmu, sub);  // multiplies (v + u)
+    fe_sub<FqP>(t, p.v, p.u);
+    mont_mul<FqP>(a, t, n1);
+    fe_add<FqP>(t, p.v, p.u);
+    mont_mul<FqP>(b, t, n2);
+    mont_mul<FqP>(c, p.t1, p.t2);
+    mont_mul<FqP>(c, c, n.t2d);
+    mont_mul<FqP>(d, p.z, n.z);
+    fe_dbl<FqP>(d, d);
+    fe cu, cv, dpc, dmc, cz, ct;
+    fe_sub<FqP>(cu, b, a);
+    fe_add<FqP>(cv, b, a);
+    fe_add<FqP>(dpc, d, c);
+    fe_sub<FqP>(dmc, d, c);
+    fe_select(cz, dpc, dmc, sub);
+    fe_select(ct, dmc, dpc, sub);
+    into_extended(r, cu, cv, cz, ct);
+}
+// p +/- n for an affine-Niels operand (n.z == 1, so d = 2z).
+JJ_DEVICE void point_add_aff_niels(ext_point& r, const ext_point& p, const aff_niels& n, bool sub) {
+    fe a, b, c, d, t, n1, n2;
+    fe_select(n1, n.vmu, n.vpu, sub);
+    fe_select(n2, n.vpu, n.vmu, sub);
+    fe_sub<FqP>(t, p.v, p.u);
+    mont_mul<FqP>(a, t, n1);
+    fe_add<FqP>(t, p.v, p.u);
+    mont_mul<FqP>(b, t, n2);
+    mont_mul<FqP>(c, p.t1, p.t2);
+    mont_mul<FqP>(c, c, n.t2d);
+    fe_dbl<FqP>(d, p.z);
+    fe cu, cv, dpc, dmc, cz, ct;
+    fe_sub<FqP>(cu, b, a);
+    fe_add<FqP>(cv, b, a);
+    fe_add<FqP>(dpc, d, c);
+    fe_sub<FqP>(dmc, d, c);
+    fe_select(cz, dpc, dmc, sub);
+    fe_select(ct, dmc, dpc, sub);
+    into_extended(r, cu, cv, cz, ct);
+}
+
+JJ_DEVICE void point_to_niels(ext_niels& n, const ext_point& p) {
+    fe d2, t;
+    JJ_LOAD_CONST(d2, Curve::D2);
+    fe_add<FqP>(n.vpu, p.v, p.u);
+    fe_sub<FqP>(n.vmu, p.v, p.u);
+    n.z = p.z;
+    mont_mul<FqP>(t, p.t1, p.t2);
+    mont_mul<FqP>(n.t2d, t, d2);
+}
+JJ_DEVICE void affine_to_niels(aff_niels& n, const aff_point& p) {
+    fe d2, t;
+    JJ_LOAD_CONST(d2, Curve::D2);
+    fe_add<FqP>(n.vpu, p.v, p.u);
+    fe_sub<FqP>(n.vmu, p.v, p.u);
+    mont_mul<FqP>(t, p.u, p.v);
+    mont_mul<FqP>(n.t2d, t, d2);
+}
+// p + q with both extended: q.to_niels() then the 8M add (src/lib.rs:992-999).
+JJ_DEVICE void point_add(ext_point& r, const ext_point& p, const ext_point& q, bool sub) {
+    ext_niels n;
+    point_to_niels(n, q);
+    point_add_niels(r, p, n, sub);
+}
+JJ_DEVICE bool point_is_identity(const ext_point& p) {  // u == 0 and v == z  src/lib.rs:691-696
+    return fe_is_zero(p.u) && fe_eq(p.v, p.z);
+}
+
+}  // namespace jj

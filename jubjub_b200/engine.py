@@ -1,0 +1,303 @@
+"""Host-side engine: one context (one GPU, one stream) over the C ABI.
+
+Arrays are numpy `uint64` with a trailing limb axis -- field elements (n, 4), ExtendedPoint
+(n, 20), AffinePoint (n, 8), ExtendedNielsPoint (n, 16), AffineNielsPoint (n, 12) -- or
+`uint8` (n, 32) byte strings, i.e. exactly the reference's in-memory layouts
+(src/lib.rs:81-84, 139-145, 255-259, 327-332; src/fr.rs:23).  `DeviceArray` keeps a batch
+resident in HBM between calls.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+FQ, FR = "fq", "fr"
+EXT_W, AFF_W, NIELS_W, ANIELS_W = 20, 8, 16, 12
+
+
+class JubjubError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{L.ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class DeviceArray:
+    """A caller-owned buffer in the context's HBM (jj_malloc); shape/dtype mirror numpy."""
+
+    def __init__(self, engine, shape, dtype):
+        self.engine, self.shape, self.dtype = engine, tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        engine._check(engine.lib.jj_malloc(engine.ctx, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def __len__(self):
+        return self.shape[0]
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.shape == self.shape, (host.shape, self.shape)
+        self.engine._check(self.engine.lib.jj_memcpy_h2d(self.engine.ctx, self.ptr, host.ctypes.data, self.nbytes))
+        return self
+
+    def download(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        self.engine._check(self.engine.lib.jj_memcpy_d2h(self.engine.ctx, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.engine.lib.jj_free(self.engine.ctx, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = L.load()
+        ctx = C.c_void_p()
+        rc = self.lib.jj_init(device, C.byref(ctx))
+        if rc != 0:
+            raise JubjubError(rc, f"jj_init(device={device}) failed -- a B200 (sm_100) device is required")
+        self.ctx, self.device = ctx, device
+
+    def close(self):
+        if self.ctx:
+            self.lib.jj_destroy(self.ctx)
+            self.ctx = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise JubjubError(rc, self.lib.jj_last_error(self.ctx).decode())
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def empty(self, shape, dtype=np.uint64):
+        return DeviceArray(self, shape, dtype)
+
+    def to_device(self, host):
+        host = np.ascontiguousarray(host)
+        return DeviceArray(self, host.shape, host.dtype).upload(host)
+
+    def _arg(self, a, width, dtype=np.uint64):
+        """-> (pointer, n, is_device, keepalive)"""
+        if isinstance(a, DeviceArray):
+            assert a.shape[1] == width and a.dtype == np.dtype(dtype), (a.shape, a.dtype, width)
+            return a.ptr, a.shape[0], True, a
+        a = np.ascontiguousarray(a, dtype=dtype)
+        if a.ndim != 2 or a.shape[1] != width:
+            raise ValueError(f"expected shape (n, {width}) {np.dtype(dtype)}, got {a.shape}")
+        return a.ctypes.data, a.shape[0], False, a
+
+    def _out(self, like_device, n, width, dtype=np.uint64, out=None):
+        if out is not None:
+            if isinstance(out, DeviceArray) != like_device:
+                raise ValueError("inputs and output must all be host arrays or all DeviceArrays")
+            return out
+        return DeviceArray(self, (n, width), dtype) if like_device else np.empty((n, width), dtype=dtype)
+
+    @staticmethod
+    def _ptr(x):
+        return x.ptr if isinstance(x, DeviceArray) else x.ctypes.data
+
+    def _call(self, name, ins, out_width, out_dtype=np.uint64, flags=0, out=None, ok=False, extra_pre=()):
+        """ins: list of (array, width, dtype).  Returns out (and ok flags when ok=True)."""
+        args, n, dev, keep = [], None, None, []
+        for a, w, dt in ins:
+            p, cnt, isdev, k = self._arg(a, w, dt)
+            if n is None:
+                n, dev = cnt, isdev
+            elif cnt != n:
+                # the reference panics on a length mismatch (assert_eq!, src/lib.rs:841)
+                raise JubjubError(-1, f"length mismatch: {cnt} != {n}")
+            elif isdev != dev:
+                raise ValueError("inputs must all be host arrays or all DeviceArrays")
+            args.append(p)
+            keep.append(k)
+        o = self._out(dev, n, out_width, out_dtype, out)
+        call = list(extra_pre) + args + [self._ptr(o)]
+        okbuf = None
+        if ok:
+            okbuf = self._out(dev, n, 1, np.uint8)
+            call.append(self._ptr(okbuf))
+        f = flags | (L.JJ_DEVICE_PTRS if dev else 0)
+        self._check(getattr(self.lib, name)(self.ctx, *call, n, f))
+        if ok:
+            return o, (okbuf if dev else okbuf.reshape(-1))
+        return o
+
+    # ---- field batches ---------------------------------------------------------------------
+    def fe_mul(self, field, a, b, flags=0, out=None):
+        return self._call(f"jj_{field}_mul", [(a, 4, np.uint64), (b, 4, np.uint64)], 4, flags=flags, out=out)
+
+    def fe_add(self, field, a, b, flags=0, out=None):
+        return self._call(f"jj_{field}_add", [(a, 4, np.uint64), (b, 4, np.uint64)], 4, flags=flags, out=out)
+
+    def fe_sub(self, field, a, b, flags=0, out=None):
+        return self._call(f"jj_{field}_sub", [(a, 4, np.uint64), (b, 4, np.uint64)], 4, flags=flags, out=out)
+
+    def fe_square(self, field, a, flags=0, out=None):
+        return self._call(f"jj_{field}_square", [(a, 4, np.uint64)], 4, flags=flags, out=out)
+
+    def fe_neg(self, field, a, flags=0, out=None):
+        return self._call(f"jj_{field}_neg", [(a, 4, np.uint64)], 4, flags=flags, out=out)
+
+    def fe_double(self, field, a, flags=0, out=None):
+        return self._call(f"jj_{field}_double", [(a, 4, np.uint64)], 4, flags=flags, out=out)
+
+    def fe_invert(self, field, a, flags=0):
+        """-> (inverse, ok): ok[i] = 0 and inverse[i] = 0 where a[i] = 0 (CtOption::none)."""
+        return self._call(f"jj_{field}_invert", [(a, 4, np.uint64)], 4, flags=flags, ok=True)
+
+    def fe_to_bytes(self, field, a):
+        return self._call(f"jj_{field}_to_bytes", [(a, 4, np.uint64)], 32, np.uint8)
+
+    def fe_from_bytes(self, field, b):
+        return self._call(f"jj_{field}_from_bytes", [(b, 32, np.uint8)], 4, ok=True)
+
+    def fe_from_bytes_wide(self, field, b64):
+        return self._call(f"jj_{field}_from_bytes_wide", [(b64, 64, np.uint8)], 4)
+
+    def fe_stream(self, field, seed, n, first=0, device=False):
+        o = self._out(device, n, 4)
+        f = L.JJ_DEVICE_PTRS if device else 0
+        self._check(getattr(self.lib, f"jj_{field}_stream")(self.ctx, seed, first, self._ptr(o), n, f))
+        return o
+
+    # ---- points ----------------------------------------------------------------------------
+    def point_double(self, p, out=None):
+        return self._call("jj_point_double", [(p, EXT_W, np.uint64)], EXT_W, out=out)
+
+    def point_add(self, p, q, subtract=False, out=None):
+        return self._call("jj_point_add", [(p, EXT_W, np.uint64), (q, EXT_W, np.uint64)], EXT_W,
+                          flags=L.JJ_SUBTRACT if subtract else 0, out=out)
+
+    def point_add_niels(self, p, q, subtract=False, out=None):
+        return self._call("jj_point_add_niels", [(p, EXT_W, np.uint64), (q, NIELS_W, np.uint64)], EXT_W,
+                          flags=L.JJ_SUBTRACT if subtract else 0, out=out)
+
+    def point_add_affine_niels(self, p, q, subtract=False, out=None):
+        return self._call("jj_point_add_affine_niels", [(p, EXT_W, np.uint64), (q, ANIELS_W, np.uint64)], EXT_W,
+                          flags=L.JJ_SUBTRACT if subtract else 0, out=out)
+
+    def point_to_niels(self, p):
+        return self._call("jj_point_to_niels", [(p, EXT_W, np.uint64)], NIELS_W)
+
+    def affine_to_niels(self, p):
+        return self._call("jj_affine_to_niels", [(p, AFF_W, np.uint64)], ANIELS_W)
+
+    @staticmethod
+    def _out_fmt(output):
+        return {"extended": (EXT_W, np.uint64, 0), "affine": (AFF_W, np.uint64, L.JJ_OUT_AFFINE),
+                "bytes": (32, np.uint8, L.JJ_OUT_BYTES)}[output]
+
+    def scalar_mul(self, points, scalars, output="extended", scalar_mont=False, out=None, flags=0):
+        """out[i] = [scalars[i]] points[i]  (`&ExtendedPoint * &Fr`, src/lib.rs:873-879)."""
+        w, dt, f = self._out_fmt(output)
+        sc = (scalars, 4, np.uint64) if scalar_mont else (scalars, 32, np.uint8)
+        return self._call("jj_scalar_mul", [(points, EXT_W, np.uint64), sc], w, dt,
+                          flags=f | flags | (L.JJ_SCALAR_MONT if scalar_mont else 0), out=out)
+
+    def scalar_mul_fixed(self, base_affine, scalars, output="extended", scalar_mont=False, out=None):
+        """out[i] = [scalars[i]] base  (`&AffinePoint * &Fr`, src/lib.rs:1109-1115), one shared base."""
+        w, dt, f = self._out_fmt(output)
+        base = np.ascontiguousarray(base_affine, dtype=np.uint64).reshape(1, AFF_W)
+        if scalar_mont:
+            p, n, dev, keep = self._arg(scalars, 4, np.uint64)
+        else:
+            p, n, dev, keep = self._arg(scalars, 32, np.uint8)
+        o = self._out(dev, n, w, dt, out)
+        bptr = base.ctypes.data
+        bdev = None
+        if dev:
+            bdev = self.to_device(base)
+            bptr = bdev.ptr
+        fl = f | (L.JJ_DEVICE_PTRS if dev else 0) | (L.JJ_SCALAR_MONT if scalar_mont else 0)
+        self._check(self.lib.jj_scalar_mul_fixed(self.ctx, bptr, p, self._ptr(o), n, fl))
+        return o
+
+    def batch_normalize(self, p, out=None):
+        return self._call("jj_batch_normalize", [(p, EXT_W, np.uint64)], AFF_W, out=out)
+
+    def affine_to_bytes(self, a, out=None):
+        return self._call("jj_affine_to_bytes", [(a, AFF_W, np.uint64)], 32, np.uint8, out=out)
+
+    def _flag(self, name, p):
+        o = self._call(name, [(p, EXT_W, np.uint64)], 1, np.uint8)
+        return o if isinstance(o, DeviceArray) else o.reshape(-1)
+
+    def is_torsion_free(self, p):
+        return self._flag("jj_is_torsion_free", p)
+
+    def is_identity(self, p):
+        return self._flag("jj_is_identity", p)
+
+    def is_small_order(self, p):
+        return self._flag("jj_is_small_order", p)
+
+    # ---- measurement helpers -----------------------------------------------------------------
+    def sync(self):
+        self._check(self.lib.jj_sync(self.ctx))
+
+    def timer_start(self):
+        self._check(self.lib.jj_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.lib.jj_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._check(self.lib.jj_flush_l2(self.ctx))
+
+    def launch_count(self):
+        return int(self.lib.jj_launch_count(self.ctx))
+
+    def imad_peak(self):
+        v = C.c_double()
+        self._check(self.lib.jj_measure_imad_peak(self.ctx, C.byref(v)))
+        return v.value
+
+    def set_scalar_mul_variant(self, v):
+        self._check(self.lib.jj_set_scalar_mul_variant(self.ctx, v))
+
+    def device_info(self):
+        sm, khz, mem = C.c_int32(), C.c_int32(), C.c_uint64()
+        self._check(self.lib.jj_device_info(self.ctx, C.byref(sm), C.byref(khz), C.byref(mem)))
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "hbm_bytes": mem.value}
+
+    # ---- multi-GPU ------------------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        rc = self.lib.jj_comm_unique_id(buf)
+        if rc != 0:
+            raise JubjubError(rc, "ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.jj_comm_init(self.ctx, nranks, rank, buf))
+
+    def scalar_mul_sharded(self, points_local, scalars_local, out_all, output="extended", async_=False):
+        """This rank's shard + all-gather of every rank's results into out_all (device)."""
+        w, dt, f = self._out_fmt(output)
+        f |= L.JJ_DEVICE_PTRS | (L.JJ_ASYNC if async_ else 0)
+        n_local = points_local.shape[0]
+        self._check(self.lib.jj_scalar_mul_sharded(self.ctx, points_local.ptr, scalars_local.ptr, out_all.ptr,
+                                                   n_local, f))
+        return out_all
+
+
+_default = None
+
+
+def default_engine():
+    global _default
+    if _default is None:
+        _default = Engine(0)
+    return _default

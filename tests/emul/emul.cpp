@@ -1,0 +1,100 @@
+// Host emulation harness -- TEST INFRASTRUCTURE ONLY.
+// Compiles the *kernel arithmetic source* (jubjub_b200/csrc/*.cuh) with a plain C++
+// compiler, the PTX carry-chain primitives replaced by C emulation (JJ_HOST_EMUL), so
+// the limb-level algorithms can be unit-tested against the oracle without a GPU.
+// Nothing in the product loads this; it is not a CPU fallback.
+#define JJ_HOST_EMUL 1
+#include <cstddef>
+#include <cstring>
+#include "../../jubjub_b200/csrc/fe.cuh"
+
+using namespace jj;
+
+template <class F>
+static void fe_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fe r;
+        switch (op) {
+            case 0: mont_mul<F>(r, a[i], b[i]); break;
+            case 1: mont_sqr<F>(r, a[i]); break;
+            case 2: fe_add<F>(r, a[i], b[i]); break;
+            case 3: fe_sub<F>(r, a[i], b[i]); break;
+            case 4: fe_neg<F>(r, a[i]); break;
+            case 5: fe_dbl<F>(r, a[i]); break;
+            case 6: fe_invert<F>(r, a[i]); break;
+            case 7: fe_to_canonical<F>(r, a[i]); break;
+            case 8: fe_from_raw<F>(r, a[i]); break;
+            default: fe_set_zero(r); r.w[0] = fe_is_canonical<F>(a[i]); break;
+        }
+        out[i] = r;
+    }
+}
+extern "C" void emul_fe_op(int which, int op, const void* a, const void* b, void* out, size_t n) {
+    if (which == 0) fe_op<FqP>(op, (const fe*)a, (const fe*)b, (fe*)out, n);
+    else fe_op<FrP>(op, (const fe*)a, (const fe*)b, (fe*)out, n);
+}
+
+#include "../../jubjub_b200/csrc/scalarmul.cuh"
+
+// op: 0 double, 1 add (ext+ext), 2 sub (ext-ext), 3 add ext-niels, 4 sub ext-niels,
+//     5 add affine-niels, 6 sub affine-niels, 7 to_niels (ext), 8 to_niels (affine), 9 neg
+extern "C" void emul_point_op(int op, const void* p_, const void* q_, void* out_, size_t n) {
+    const ext_point* p = (const ext_point*)p_;
+    for (size_t i = 0; i < n; i++) {
+        ext_point r;
+        switch (op) {
+            case 0: point_double(r, p[i]); break;
+            case 1: point_add(r, p[i], ((const ext_point*)q_)[i], false); break;
+            case 2: point_add(r, p[i], ((const ext_point*)q_)[i], true); break;
+            case 3: point_add_niels(r, p[i], ((const ext_niels*)q_)[i], false); break;
+            case 4: point_add_niels(r, p[i], ((const ext_niels*)q_)[i], true); break;
+            case 5: point_add_aff_niels(r, p[i], ((const aff_niels*)q_)[i], false); break;
+            case 6: point_add_aff_niels(r, p[i], ((const aff_niels*)q_)[i], true); break;
+            case 7: point_to_niels(((ext_niels*)out_)[i], p[i]); continue;
+            case 8: affine_to_niels(((aff_niels*)out_)[i], ((const aff_point*)p_)[i]); continue;
+            default: point_neg(r, p[i]); break;
+        }
+        ((ext_point*)out_)[i] = r;
+    }
+}
+extern "C" void emul_scalar_mul(const void* p_, const void* k_, void* out_, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        LocalTable tbl;
+        ext_point acc;
+        scalar_mul_core(acc, ((const ext_point*)p_)[i], ((const uint32_t*)k_) + 8 * i, tbl);
+        ((ext_point*)out_)[i] = acc;
+    }
+}
+// table[(i*8+j)*24 ..] = affine-Niels((j+1) * 16^i * base)
+extern "C" void emul_fixed_table(const void* base_affine, uint32_t* table) {
+    ext_point B;
+    point_from_affine(B, *(const aff_point*)base_affine);
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 8; j++) {
+            // (j+1) * 16^i = 16 * ((j+1) * 16^(i-1)): keeps the scalar below 2^252
+            uint32_t k[8] = {0};
+            int sh = i > 0 ? i - 1 : 0;
+            k[sh / 8] = (uint32_t)(j + 1) << (4 * (sh % 8));
+            LocalTable tbl;
+            ext_point acc;
+            scalar_mul_core(acc, B, k, tbl);
+            if (i > 0)
+                for (int d = 0; d < 4; d++) point_double(acc, acc);
+            fe zi;
+            fe_invert<FqP>(zi, acc.z);
+            aff_point a;
+            mont_mul<FqP>(a.u, acc.u, zi);
+            mont_mul<FqP>(a.v, acc.v, zi);
+            aff_niels nn;
+            affine_to_niels(nn, a);
+            std::memcpy(table + (i * 8 + j) * 24, &nn, 96);
+        }
+}
+extern "C" void emul_scalar_mul_fixed(const uint32_t* table, const void* k_, void* out_, size_t n) {
+    fixed_table_view v{table};
+    for (size_t i = 0; i < n; i++) {
+        ext_point acc;
+        scalar_mul_fixed_core(acc, ((const uint32_t*)k_) + 8 * i, v);
+        ((ext_point*)out_)[i] = acc;
+    }
+}

@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- run on the B200 box:
+    python -m pytest tests -m gpu
+Bit-exact everywhere: Montgomery limbs for field ops, all 160 bytes for point add/double
+(same formula sequence as the reference), normalised affine / 32-byte encodings for scalar-mul
+(windowed vs the reference's bitwise ladder differ projectively only)."""
+import numpy as np
+import pytest
+
+from oracle import model as M
+from tests.golden import reference_kats as K
+from tests.helpers import affine_raw, b32, fe, fe_int, scalar_bytes
+
+pytestmark = pytest.mark.gpu
+
+FQ, FR = 0, 1
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import jubjub_b200 as jj
+
+    e = jj.Engine(0)
+    yield e
+    e.close()
+
+
+def _edge_fe(m):
+    vals = [0, 1, 2, m - 1, m - 2, M.to_mont(1, m), M.to_mont(m - 1, m), (1 << 255) % m, 2**32 - 1, 2**64 - 1,
+            m >> 1, 1 << 32, 1 << 64, 1 << 224, (1 << 128) - 1]
+    return np.array([M.limbs(v) for v in vals], dtype=np.uint64)
+
+
+def _field_inputs(oracle, which, n=20000):
+    m = M.Q if which == FQ else M.R_ORDER
+    e = _edge_fe(m)
+    a = np.concatenate([e, oracle.fe_stream(which, M.SEED0, n)])
+    b = np.concatenate([e[::-1], oracle.fe_stream(which, M.SEED0 + 1, n)])
+    return a, b
+
+
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_field_ops_montgomery(eng, oracle, which, name):
+    a, b = _field_inputs(oracle, which)
+    assert (eng.fe_mul(name, a, b) == oracle.fe_batch(which, oracle.OP_MUL, a, b)).all()
+    assert (eng.fe_add(name, a, b) == oracle.fe_batch(which, oracle.OP_ADD, a, b)).all()
+    assert (eng.fe_sub(name, a, b) == oracle.fe_batch(which, oracle.OP_SUB, a, b)).all()
+    assert (eng.fe_square(name, a) == oracle.fe_batch(which, oracle.OP_SQUARE, a)).all()
+    assert (eng.fe_neg(name, a) == oracle.fe_batch(which, oracle.OP_NEG, a)).all()
+    assert (eng.fe_double(name, a) == oracle.fe_batch(which, oracle.OP_DOUBLE, a)).all()
+
+
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_field_ops_canonical_flag(eng, oracle, which, name):
+    import jubjub_b200 as jj
+
+    m = M.Q if which == FQ else M.R_ORDER
+    a, b = _field_inputs(oracle, which, 2000)
+    ca, cb = oracle.fe_to_bytes(which, a).view(np.uint64), oracle.fe_to_bytes(which, b).view(np.uint64)
+    got = eng.fe_mul(name, ca, cb, flags=jj.JJ_CANON)
+    for i in range(0, len(a), 97):
+        assert M.from_limbs(got[i]) == M.from_limbs(ca[i]) * M.from_limbs(cb[i]) % m
+    want = oracle.fe_to_bytes(which, oracle.fe_batch(which, oracle.OP_MUL, a, b)).view(np.uint64)
+    assert (got == want).all()
+    got = eng.fe_sub(name, ca, cb, flags=jj.JJ_CANON)
+    assert (got == oracle.fe_to_bytes(which, oracle.fe_batch(which, oracle.OP_SUB, a, b)).view(np.uint64)).all()
+
+
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_field_invert_and_bytes(eng, oracle, which, name):
+    m = M.Q if which == FQ else M.R_ORDER
+    a, _ = _field_inputs(oracle, which, 3000)
+    inv, ok = eng.fe_invert(name, a)
+    winv, wok = oracle.fe_invert(which, a)
+    assert (ok == wok).all() and ok[0] == 0  # zero has no inverse (CtOption::none, src/fr.rs:539)
+    assert (inv == winv).all()
+    assert (eng.fe_to_bytes(name, a) == oracle.fe_to_bytes(which, a)).all()
+    # from_bytes: canonical accepted, >= m rejected (src/fr.rs:925-960)
+    enc = np.concatenate([oracle.fe_to_bytes(which, a),
+                          scalar_bytes(m, m + 1, (1 << 256) - 1, m - 1, 0)])
+    got, ok = eng.fe_from_bytes(name, enc)
+    want, wok = oracle.fe_from_bytes(which, enc)
+    assert (ok == wok).all() and ok[-5:].tolist() == [0, 0, 0, 1, 1]
+    assert (got[ok == 1] == want[ok == 1]).all()
+
+
+def test_fr_reference_kats_on_gpu(eng, oracle):
+    """src/fr.rs:1045-1099 (LARGEST add/neg/sub), :1024-1034 (wide max), :1758-1776 (a*b==c)."""
+    big, one_raw = fe(K.FR_LARGEST), fe([1, 0, 0, 0])
+    assert (eng.fe_add("fr", big, big) == fe(K.FR_LARGEST_PLUS_LARGEST)).all()
+    assert (eng.fe_add("fr", big, one_raw) == 0).all()
+    assert (eng.fe_neg("fr", big) == one_raw).all()
+    assert (eng.fe_neg("fr", fe([0, 0, 0, 0])) == 0).all()
+    assert (eng.fe_sub("fr", big, big) == 0).all()
+    assert (eng.fe_mul("fr", fe(K.MULC_A), fe(K.MULC_B)) == fe(K.MULC_C)).all()
+    assert (eng.fe_from_bytes_wide("fr", np.full((1, 64), 0xFF, np.uint8)) == fe(K.FR_WIDE_MAX_MONT)).all()
+    assert (eng.fe_to_bytes("fr", fe(K.FR_R2)) == b32(K.FR_BYTES_R2)).all()
+    _, ok = eng.fe_from_bytes("fr", b32(*K.FR_BYTES_REJECTED))
+    assert ok.tolist() == [0, 0, 0, 0]
+
+
+def test_fq_bench_vectors(eng, oracle):
+    """benches/fq_bench.rs:25-33: n *= -1 alternates between -1 and 1."""
+    one = oracle.fe_one(FQ)
+    neg_one = eng.fe_neg("fq", one)
+    n = one
+    for i in range(6):
+        n = eng.fe_mul("fq", n, neg_one)
+        assert (n == (neg_one if i % 2 == 0 else one)).all()
+    four = eng.fe_double("fq", eng.fe_double("fq", one))
+    inv, ok = eng.fe_invert("fq", four)
+    assert ok[0] == 1 and (eng.fe_mul("fq", inv, four) == one).all()
+
+
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_stream_and_wide(eng, oracle, which, name):
+    n = 5000
+    assert (eng.fe_stream(name, M.SEED0 + 2, n, first=12345) == oracle.fe_stream(which, M.SEED0 + 2, n, first=12345)).all()
+    rng = np.random.default_rng(7)
+    wide = rng.integers(0, 256, size=(n, 64), dtype=np.uint8)
+    wide[0] = 0xFF
+    wide[1] = 0
+    assert (eng.fe_from_bytes_wide(name, wide) == oracle.fe_from_bytes_wide(which, wide)).all()
+
+
+# ------------------------------------------------------------------------------ points
+def _points(oracle, n, seed=M.SEED0 + 3):
+    """n full-order points [t_i] G as extended with z = 1, plus identity and the 8-torsion points."""
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, seed, n))
+    g = oracle.affine_to_extended(oracle.generator())
+    rnd = oracle.scalar_mul(np.repeat(g, n, axis=0), t)
+    tors = oracle.affine_to_extended(affine_raw(oracle, K.EIGHT_TORSION_RAW))
+    return np.concatenate([oracle.identity(), tors, rnd])
+
+
+def test_point_ops_bit_exact(eng, oracle):
+    p = _points(oracle, 600)
+    q = oracle.ext_double(p[::-1].copy())  # non-trivial z
+    assert (eng.point_double(p) == oracle.ext_double(p)).all()
+    assert (eng.point_double(q) == oracle.ext_double(q)).all()
+    assert (eng.point_add(q, p) == oracle.ext_add(q, p)).all()
+    assert (eng.point_add(q, p, subtract=True) == oracle.ext_sub(q, p)).all()
+    nq = oracle.ext_to_niels(q)
+    assert (eng.point_to_niels(q) == nq).all()
+    assert (eng.point_add_niels(p, nq) == oracle.ext_add_niels(p, nq)).all()
+    assert (eng.point_add_niels(p, nq, subtract=True) == oracle.ext_sub_niels(p, nq)).all()
+    an = oracle.affine_to_niels(oracle.batch_normalize(q))
+    assert (eng.affine_to_niels(oracle.batch_normalize(q)) == an).all()
+    assert (eng.point_add_affine_niels(p, an) == oracle.ext_add_affine_niels(p, an)).all()
+    assert (eng.point_add_affine_niels(p, an, subtract=True) == oracle.ext_sub_affine_niels(p, an)).all()
+
+
+def test_point_bench_vectors(eng, oracle):
+    """benches/point_bench.rs: identity doubling / identity + (-identity) / cached adds."""
+    ident = oracle.identity()
+    assert oracle.is_identity(eng.point_double(ident))[0]
+    assert oracle.is_identity(eng.point_add(ident, oracle.ext_neg(ident)))[0]
+    assert (eng.point_add_niels(ident, oracle.ext_to_niels(ident)) == oracle.ext_add_niels(ident, oracle.ext_to_niels(ident))).all()
+    an = oracle.affine_to_niels(oracle.ext_to_affine(ident))
+    assert (eng.point_add_affine_niels(ident, an) == oracle.ext_add_affine_niels(ident, an)).all()
+
+
+EDGE_SCALARS = [0, 1, 2, 7, 8, 9, 15, 16, 17, M.R_ORDER - 1, M.R_ORDER, M.R_ORDER + 1, (1 << 252) - 1, (1 << 252),
+                (1 << 256) - 1, int("8" * 64, 16), int("7" * 64, 16), int("f" * 63, 16), 1 << 251, 0x88, 0x80]
+
+
+def _smul_case(oracle, n):
+    p = _points(oracle, n)
+    k = np.concatenate([scalar_bytes(*EDGE_SCALARS),
+                        oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 2, len(p)))])[: len(p)]
+    return p, k
+
+
+@pytest.mark.parametrize("variant", list(range(0, 11)))
+def test_scalar_mul_variants(eng, oracle, variant):
+    eng.set_scalar_mul_variant(variant)
+    try:
+        p, k = _smul_case(oracle, 1200 if variant == 0 else 300)
+        want_ext = oracle.scalar_mul(p, k)
+        want_aff = oracle.batch_normalize(want_ext)
+        got = eng.scalar_mul(p, k)
+        assert oracle.ext_eq(got, want_ext).all()  # projective equality, src/lib.rs:153-163
+        assert (oracle.batch_normalize(got) == want_aff).all()
+        assert (eng.scalar_mul(p, k, output="affine") == want_aff).all()
+        assert (eng.scalar_mul(p, k, output="bytes") == oracle.affine_to_bytes(want_aff)).all()
+    finally:
+        eng.set_scalar_mul_variant(0)
+
+
+def test_scalar_mul_vs_bigint_model(eng, oracle):
+    p, k = _smul_case(oracle, 40)
+    vals = oracle.fe_to_bytes(FQ, oracle.batch_normalize(p).reshape(-1, 4)).reshape(-1, 64)
+    got = eng.scalar_mul(p, k, output="bytes")
+    for i in range(len(p)):
+        u = int.from_bytes(bytes(vals[i, :32]), "little")
+        v = int.from_bytes(bytes(vals[i, 32:]), "little")
+        assert bytes(got[i]) == M.encode(M.pmul((u, v), M.scalar_from_bytes_ref(bytes(k[i])))), i
+
+
+def test_scalar_mul_montgomery_scalars(eng, oracle):
+    """`&ExtendedPoint * &Fr` takes the scalar in Montgomery form and calls to_bytes (src/lib.rs:877)."""
+    p = _points(oracle, 200)
+    s = oracle.fe_stream(FR, 99, len(p))
+    got = eng.scalar_mul(p, s, scalar_mont=True, output="affine")
+    assert (got == oracle.batch_normalize(oracle.scalar_mul(p, oracle.fe_to_bytes(FR, s)))).all()
+
+
+def test_mul_consistency_and_assoc(eng, oracle):
+    """src/lib.rs:1505-1527, :1757-1804 with the reference's fixed raw-limb scalars."""
+    p = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(affine_raw(oracle, [K.TEST_POINT_RAW])))
+    a, b, c = fe(K.MULC_A), fe(K.MULC_B), fe(K.MULC_C)
+    assert (eng.fe_mul("fr", a, b) == c).all()
+    pc = eng.scalar_mul(p, c, scalar_mont=True)
+    pab = eng.scalar_mul(eng.scalar_mul(p, a, scalar_mont=True), b, scalar_mont=True)
+    assert oracle.ext_eq(pc, pab)[0]
+    assert (eng.batch_normalize(pc) == eng.batch_normalize(pab)).all()
+    aff = eng.batch_normalize(p)
+    assert (eng.scalar_mul_fixed(aff, c, scalar_mont=True, output="affine") == eng.batch_normalize(pab)).all()
+    lhs = eng.scalar_mul(eng.scalar_mul(p, scalar_bytes(1000)), scalar_bytes(3938))
+    assert oracle.ext_eq(lhs, eng.scalar_mul(p, scalar_bytes(3938000)))[0]
+
+
+def test_scalar_mul_fixed(eng, oracle):
+    k = np.concatenate([scalar_bytes(*EDGE_SCALARS), oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 5, 2000))])
+    for base in (oracle.generator(), oracle.ext_to_affine(oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator())))):
+        want = oracle.batch_normalize(oracle.scalar_mul_fixed(base, k))
+        assert (eng.scalar_mul_fixed(base, k, output="affine") == want).all()
+        assert (eng.batch_normalize(eng.scalar_mul_fixed(base, k)) == want).all()
+        assert (eng.scalar_mul_fixed(base, k, output="bytes") == oracle.affine_to_bytes(want)).all()
+
+
+def test_serialization_golden(eng, oracle):
+    """src/lib.rs:1807-1890: encodings of k * (8 G), k = 1..16."""
+    g8 = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator()))
+    want = b32(*K.SERIALIZED_MULTIPLES_OF_8G)
+    k = scalar_bytes(*range(1, 17))
+    assert (eng.scalar_mul(np.repeat(g8, 16, axis=0), k, output="bytes") == want).all()
+    assert (eng.scalar_mul_fixed(oracle.ext_to_affine(g8), k, output="bytes") == want).all()
+    # and by repeated addition, as the reference test walks it
+    p = g8
+    for i in range(16):
+        assert (eng.affine_to_bytes(eng.batch_normalize(p))[0] == want[i]).all(), i
+        p = eng.point_add(p, g8)
+
+
+def test_batch_normalize_and_flags(eng, oracle):
+    p = _points(oracle, 700)
+    q = oracle.ext_double(oracle.ext_double(p))
+    q[5, 8:12] = 0  # z = 0 is skipped like ff::BatchInverter and yields (0, 0)
+    want = oracle.batch_normalize(q)
+    got = eng.batch_normalize(q)
+    assert (got == want).all() and (got[5] == 0).all()
+    assert (eng.affine_to_bytes(got) == oracle.affine_to_bytes(want)).all()
+    # src/lib.rs:1530-1575: p, 2p, 4p, ... normalised in a batch == one inversion each
+    pt = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(affine_raw(oracle, [K.TEST_POINT_RAW])))
+    v = []
+    for _ in range(10):
+        v.append(pt[0].copy())
+        pt = eng.point_double(pt)
+    v = np.array(v)
+    assert (eng.batch_normalize(v) == oracle.ext_to_affine(v)).all()
+    # 8-torsion: small order, [8]T = identity, not torsion free except identity (src/lib.rs:1680-1754)
+    tors = oracle.affine_to_extended(affine_raw(oracle, K.EIGHT_TORSION_RAW))
+    assert eng.is_small_order(tors).all()
+    c = eng.point_double(eng.point_double(eng.point_double(tors)))
+    assert eng.is_identity(c).all()
+    assert (eng.is_identity(p[:20]) == oracle.is_identity(p[:20])).all()
+    assert (eng.is_torsion_free(p[:40]) == oracle.is_torsion_free(p[:40])).all()
+    g8 = oracle.ext_mul_by_cofactor(p[9:30])
+    assert eng.is_torsion_free(g8).all()
+    assert (eng.is_small_order(p[:40]) == oracle.is_small_order(p[:40])).all()
+
+
+def test_find_eight_torsion_on_gpu(eng, oracle):
+    """src/lib.rs:1680-1696: [r] G walks the 8-torsion subgroup."""
+    g = oracle.affine_to_extended(affine_raw(oracle, [K.FULL_GENERATOR_RAW]))
+    t = eng.scalar_mul(g, b32(K.FR_MODULUS_BYTES))
+    want = affine_raw(oracle, K.EIGHT_TORSION_RAW)
+    cur = t
+    for i in range(8):
+        assert (eng.batch_normalize(cur) == want[i]).all(), i
+        cur = eng.point_add(cur, t)
+
+
+# ------------------------------------------------------------------------------ residency, sizes, errors
+def test_device_resident_and_in_place(eng, oracle):
+    a, b = _field_inputs(oracle, FQ, 4096)
+    da, db = eng.to_device(a), eng.to_device(b)
+    out = eng.fe_mul("fq", da, db, out=da)  # in place, like MulAssign (src/util.rs:126-152)
+    assert out is da and (da.download() == oracle.fe_batch(FQ, oracle.OP_MUL, a, b)).all()
+    p, k = _smul_case(oracle, 500)
+    dp, dk = eng.to_device(p), eng.to_device(k)
+    got = eng.scalar_mul(dp, dk, output="affine").download()
+    assert (got == oracle.batch_normalize(oracle.scalar_mul(p, k))).all()
+    dd = eng.point_double(dp, out=dp)
+    assert (dd.download() == oracle.ext_double(p)).all()
+
+
+def test_empty_ragged_and_chunk_boundaries(eng, oracle):
+    assert eng.fe_mul("fq", np.zeros((0, 4), np.uint64), np.zeros((0, 4), np.uint64)).shape == (0, 4)
+    assert eng.scalar_mul(np.zeros((0, 20), np.uint64), np.zeros((0, 32), np.uint8)).shape == (0, 20)
+    for n in (1, 31, 33, (1 << 17) - 1, (1 << 17) + 1, 3 * (1 << 17) + 5):  # staging chunk is 2^17 units
+        a, b = oracle.fe_stream(FQ, 1, n), oracle.fe_stream(FQ, 2, n)
+        assert (eng.fe_mul("fq", a, b) == oracle.fe_batch(FQ, oracle.OP_MUL, a, b)).all(), n
+    p, k = _smul_case(oracle, 70)
+    for n in (1, 31, 33, 79):
+        assert (eng.scalar_mul(p[:n], k[:n], output="affine") == oracle.batch_normalize(oracle.scalar_mul(p[:n], k[:n]))).all()
+
+
+def test_error_behaviour(eng, oracle):
+    import ctypes as C
+
+    import jubjub_b200 as jj
+
+    a = oracle.fe_stream(FQ, 1, 8)
+    with pytest.raises(jj.JubjubError) as e:  # the reference panics on length mismatch (src/lib.rs:841)
+        eng.fe_mul("fq", a, a[:4])
+    assert e.value.code == -1
+    assert eng.lib.jj_fq_mul(eng.ctx, None, a.ctypes.data, a.ctypes.data, 8, 0) == -1
+    d = eng.to_device(a)
+    assert eng.lib.jj_fq_mul(eng.ctx, d.ptr + 8, d.ptr, d.ptr, 4, jj.JJ_DEVICE_PTRS) == -1  # misaligned
+    assert b"aligned" in eng.lib.jj_last_error(eng.ctx)
+    assert eng.lib.jj_set_scalar_mul_variant(eng.ctx, 99) == -1
+    ctx = C.c_void_p()
+    assert eng.lib.jj_init(10_000, C.byref(ctx)) == -1
+
+
+def test_full_size_linearity_1m(eng, oracle):
+    """BASELINE config 3 size (2^20 units): [a]P + [b]P == [a + b]P on the prime-order subgroup,
+    every unit checked on the device path; a 512-unit sample is re-checked against the oracle."""
+    n = 1 << 20
+    g8 = oracle.ext_to_affine(oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator())))
+    t = eng.fe_to_bytes("fr", eng.fe_stream("fr", M.SEED0 + 3, n, device=True))
+    pts = eng.scalar_mul_fixed(g8, t)  # P_i = [t_i] 8G, device resident
+    a = eng.fe_stream("fr", M.SEED0 + 2, n, device=True)
+    b = eng.fe_stream("fr", M.SEED0 + 4, n, device=True)
+    ab = eng.fe_add("fr", a, b)
+    pa = eng.scalar_mul(pts, a, scalar_mont=True)
+    pb = eng.scalar_mul(pts, b, scalar_mont=True)
+    lhs = eng.batch_normalize(eng.point_add(pa, pb)).download()
+    rhs = eng.scalar_mul(pts, ab, scalar_mont=True, output="affine").download()
+    assert (lhs == rhs).all()
+    idx = np.arange(0, n, n // 512)[:512]
+    ph, ah = pts.download()[idx], oracle.fe_to_bytes(FR, a.download()[idx])
+    assert (eng.batch_normalize(pa).download()[idx] == oracle.batch_normalize(oracle.scalar_mul(ph, ah))).all()

@@ -1,0 +1,141 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+product fails loudly without a GPU, and the kernel arithmetic source (compiled for the host with
+the PTX primitives emulated, tests/emul) matches the oracle limb for limb."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import model as M
+from tests.helpers import scalar_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FQ, FR = 0, 1
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+
+    g.build()
+    return g
+
+
+def test_header_symbols_exported(built):
+    from jubjub_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "jubjub_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(jj_[a-z0-9_]+)\s*\(", header)) - {"jj_ctx"})
+    lib = C.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(_lib.ALL_SYMBOLS) == declared  # the Python binding covers the whole header
+
+
+def test_product_fails_loudly_without_gpu(built):
+    import torch
+
+    import jubjub_b200 as jj
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(jj.JubjubError) as e:
+        jj.Engine(0)
+    assert e.value.code == -5  # JJ_ERR_NO_DEVICE: there is no CPU fallback
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jubjub_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                # no import, include, dlopen or link of anything under oracle/
+                assert not re.search(r"import\s+oracle|from\s+oracle|#include[^\n]*oracle|jj_oracle|libjj_oracle", src), f
+
+
+@pytest.fixture(scope="module")
+def emul(built):
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libjj_emul.so"))
+
+    class E:
+        @staticmethod
+        def fe(which, op, a, b=None):
+            a = np.ascontiguousarray(a, dtype=np.uint64)
+            b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+            out = np.empty_like(a)
+            lib.emul_fe_op(which, op, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                           out.ctypes.data_as(C.c_void_p), C.c_size_t(len(a)))
+            return out
+
+        @staticmethod
+        def pt(op, p, q, width=20):
+            out = np.empty((len(p), width), dtype=np.uint64)
+            lib.emul_point_op(op, p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p),
+                              out.ctypes.data_as(C.c_void_p), C.c_size_t(len(p)))
+            return out
+
+        @staticmethod
+        def smul(p, k):
+            out = np.empty_like(p)
+            lib.emul_scalar_mul(p.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),
+                                out.ctypes.data_as(C.c_void_p), C.c_size_t(len(p)))
+            return out
+
+        @staticmethod
+        def smul_fixed(base, k):
+            tbl = np.zeros(64 * 8 * 24, dtype=np.uint32)
+            lib.emul_fixed_table(base.ctypes.data_as(C.c_void_p), tbl.ctypes.data_as(C.c_void_p))
+            out = np.empty((len(k), 20), dtype=np.uint64)
+            lib.emul_scalar_mul_fixed(tbl.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),
+                                      out.ctypes.data_as(C.c_void_p), C.c_size_t(len(k)))
+            return out
+
+    return E
+
+
+@pytest.mark.parametrize("which", [FQ, FR])
+def test_emulated_field_arithmetic(emul, oracle, which):
+    m = M.Q if which == FQ else M.R_ORDER
+    edge = np.array([M.limbs(x) for x in (0, 1, m - 1, m - 2, M.to_mont(1, m), M.to_mont(m - 1, m), (1 << 255) % m,
+                                          2**32 - 1, 2**64 - 1, m >> 1, 1 << 32, 1 << 64, 1 << 224)], dtype=np.uint64)
+    a = np.concatenate([edge, oracle.fe_stream(which, 1, 20000)])
+    b = np.concatenate([edge[::-1], oracle.fe_stream(which, 2, 20000)])
+    for op in range(6):
+        assert (emul.fe(which, op, a, b) == oracle.fe_batch(which, op, a, b)).all(), op
+    assert (emul.fe(which, 6, a[:200]) == oracle.fe_invert(which, a[:200])[0]).all()
+    assert (emul.fe(which, 7, a) == oracle.fe_to_bytes(which, a).view(np.uint64)).all()
+    raw = np.concatenate([a, np.full((3, 4), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)])
+    assert (emul.fe(which, 8, raw) == oracle.fe_from_raw(which, raw)).all()
+    assert (emul.fe(which, 9, raw)[:, 0] == oracle.fe_from_bytes(which, raw.view(np.uint8).reshape(-1, 32))[1]).all()
+
+
+def test_emulated_points_and_scalar_mul(emul, oracle):
+    n = 48
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 3, n))
+    p = oracle.scalar_mul(np.repeat(g, n, axis=0), t)
+    q = oracle.ext_double(p[::-1].copy())
+    assert (emul.pt(0, p, p) == oracle.ext_double(p)).all()
+    assert (emul.pt(1, p, q) == oracle.ext_add(p, q)).all()
+    assert (emul.pt(2, p, q) == oracle.ext_sub(p, q)).all()
+    nq = oracle.ext_to_niels(q)
+    assert (emul.pt(7, q, q, 16) == nq).all()
+    assert (emul.pt(3, p, nq) == oracle.ext_add_niels(p, nq)).all()
+    assert (emul.pt(4, p, nq) == oracle.ext_sub_niels(p, nq)).all()
+    aq = oracle.ext_to_affine(q)
+    anq = oracle.affine_to_niels(aq)
+    assert (emul.pt(8, aq, aq, 12) == anq).all()
+    assert (emul.pt(5, p, anq) == oracle.ext_add_affine_niels(p, anq)).all()
+    assert (emul.pt(6, p, anq) == oracle.ext_sub_affine_niels(p, anq)).all()
+    edge = [0, 1, 2, 7, 8, 9, 15, 16, M.R_ORDER - 1, M.R_ORDER, (1 << 252) - 1, (1 << 256) - 1, int("8" * 64, 16),
+            int("7" * 64, 16)]
+    k = np.concatenate([scalar_bytes(*edge), oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 2, n))])
+    pp = np.concatenate([np.repeat(p[:1], len(edge), axis=0), p])
+    want = oracle.scalar_mul(pp, k)
+    got = emul.smul(pp, k)
+    assert oracle.ext_eq(got, want).all()
+    assert (oracle.batch_normalize(got) == oracle.batch_normalize(want)).all()
+    got = emul.smul_fixed(oracle.generator(), k)
+    assert (oracle.batch_normalize(got) == oracle.batch_normalize(oracle.scalar_mul_fixed(oracle.generator(), k))).all()
