@@ -150,7 +150,7 @@ const SmulVariant kVariants[] = {
     {64, 6, TABLE_GMEM},       // 10: 12 warps/SM in 6 blocks
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 3;
+constexpr int kDefaultVariant = 5;
 
 template <int T, int MB, int TAB>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, size_t sc_stride, char* out,
@@ -521,18 +521,18 @@ int32_t jj_measure_imad_peak(jj_ctx* c, double* imad_per_sec) {
     CU(c, cudaSetDevice(c->device));
     int32_t rc = ensure(c, &c->tmp2, &c->tmp2_cap, 64);
     if (rc) return rc;
-    const int iters = 20000, blocks = c->sm_count * 8;
+    const int iters = 20000, blocks = c->sm_count * 4;
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {  // first pass is warm-up
         CU(c, cudaEventRecord(c->ev0, c->stream));
-        k_imad_peak<<<blocks, 256, 0, c->stream>>>((uint64_t*)c->tmp2, 12345u + rep, iters);
+        k_imad_peak<<<blocks, 256, 0, c->stream>>>((uint32_t*)c->tmp2, 12345u + rep, iters);
         CU(c, cudaEventRecord(c->ev1, c->stream));
         CU(c, cudaEventSynchronize(c->ev1));
         float ms = 0;
         CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         if (rep > 0) best = std::min(best, ms);
     }
-    *imad_per_sec = (double)blocks * 256.0 * iters * 64.0 / (best * 1e-3);
+    *imad_per_sec = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3);
     return JJ_OK;
 }
 

@@ -372,26 +372,34 @@ __global__ void __launch_bounds__(256) k_affine_to_bytes(const char* __restrict_
     }
 }
 
-// Integer-pipe peak probe: register-only, 16 independent IMAD.WIDE.U32 accumulators per
-// thread (the unit the scalar-mul roofline is counted in).
-__global__ void __launch_bounds__(256) k_imad_peak(uint64_t* sink, uint32_t seed, int iters) {
-    uint64_t acc[16];
-    uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+// Integer-multiplier peak probe: register-only, 8 independent accumulate chains per thread of
+// IMAD.WIDE.U32 (32x32+64 -> 64), the instruction the Montgomery kernels are made of and the
+// unit the scalar-mul roofline is counted in.  The multiplicand is the
+// chain's own previous low word, so ptxas cannot hoist or strength-reduce the products.
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, uint32_t seed, int iters) {
+    uint32_t lo[8], hi[8];
+    const uint32_t a = seed * 2654435761u + threadIdx.x * 40503u + blockIdx.x;
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = (uint64_t)k * seed;
+    for (int k = 0; k < 8; k++) {
+        lo[k] = seed + 977u * k + threadIdx.x;
+        hi[k] = seed ^ (k << 8);
+    }
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int rep = 0; rep < 4; rep++) {
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+            for (int k = 0; k < 8; k++) {
+                uint32_t m = lo[k];
+                mad_lo_cc(lo[k], a, m, lo[k]);
+                madc_hi(hi[k], a, m, hi[k]);
+            }
         }
     }
-    uint64_t x = 0;
+    uint32_t x = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) x ^= acc[k];
-    if (x == 0x1234567) sink[0] = x;  // never true in practice; keeps the chain alive
+    for (int k = 0; k < 8; k++) x ^= lo[k] ^ hi[k];
+    if (x == 0x1234567u) sink[0] = x;  // keeps the chains alive
 }
 
 // Writes a buffer larger than L2 (bench.py's flush between timed iterations).
