@@ -3,5 +3,6 @@ jubjub::{Fq, Fr, AffinePoint, ExtendedPoint, ...} surface over the C ABI in incl
 from ._lib import (JJ_ASYNC, JJ_CANON, JJ_DEVICE_PTRS, JJ_OUT_AFFINE, JJ_OUT_BYTES, JJ_SCALAR_MONT,  # noqa: F401
                    JJ_SUBTRACT, LIB_PATH)
 from .engine import FQ, FR, DeviceArray, Engine, JubjubError, default_engine  # noqa: F401
+from .sharding import equal_shards, gather_offsets, shard_range  # noqa: F401
 
 __all__ = ["Engine", "DeviceArray", "JubjubError", "default_engine", "FQ", "FR", "LIB_PATH"]

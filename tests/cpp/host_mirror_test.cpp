@@ -1,0 +1,51 @@
+// Exercises include/jubjub_b200.hpp on the GPU box (built by __graft_entry__.build(), run by
+// tests/test_gpu_cpp_mirror.py).  Reads points/scalars/expected encodings from a binary file
+// written by the Python test (expected values come from the oracle) and checks the C++ path.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+#include "../../include/jubjub_b200.hpp"
+
+using namespace jubjub;
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    std::ifstream f(argv[1], std::ios::binary);
+    uint64_t n = 0;
+    f.read((char*)&n, 8);
+    std::vector<ExtendedPoint> p(n);
+    std::vector<Fr> k(n);
+    std::vector<std::array<uint8_t, 32>> want(n);
+    f.read((char*)p.data(), n * sizeof(ExtendedPoint));
+    f.read((char*)k.data(), n * sizeof(Fr));
+    f.read((char*)want.data(), n * 32);
+    if (!f) return 3;
+    try {
+        Engine eng(0);
+        auto prod = eng.batch_mul(p, k);                       // (p * k) element-wise
+        auto enc = eng.batch_to_bytes(eng.batch_normalize(prod));
+        for (uint64_t i = 0; i < n; i++)
+            if (std::memcmp(enc[i].data(), want[i].data(), 32) != 0) {
+                std::printf("mismatch at %llu\n", (unsigned long long)i);
+                return 1;
+            }
+        // p + p == p.double() (projectively): compare through normalisation
+        auto a = eng.batch_normalize(eng.batch_add(p, p));
+        auto d = eng.batch_normalize(eng.batch_double(p));
+        if (std::memcmp(a.data(), d.data(), n * sizeof(AffinePoint)) != 0) return 4;
+        bool threw = false;
+        try {
+            k.pop_back();
+            eng.batch_mul(p, k);
+        } catch (const Error& e) {
+            threw = e.code == JJ_ERR_INVALID_ARG;
+        }
+        if (!threw) return 5;
+    } catch (const Error& e) {
+        std::printf("error %d: %s\n", e.code, e.what());
+        return 6;
+    }
+    std::printf("cpp mirror ok: %llu scalar-muls\n", (unsigned long long)n);
+    return 0;
+}
