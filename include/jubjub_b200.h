@@ -10,8 +10,8 @@
  * Data layout (all little-endian):
  *   field element     32 B = 4 x u64 limbs.  Default: the reference's internal Montgomery
  *                     form, i.e. what `Fr(pub(crate) [u64; 4])` (src/fr.rs:23) / bls12_381::Scalar
- *                     hold.  With JJ_CANON: canonical integers < m, i.e. `to_bytes()` form
- *                     (src/fr.rs:296-308); canonical inputs >= m are rejected per element.
+ *                     hold.  With JJ_CANON: canonical integers, i.e. `to_bytes()` form
+ *                     (src/fr.rs:296-308); inputs >= m are reduced mod m as `from_raw` does (:347-349).
  *   ExtendedPoint     160 B = (u, v, z, t1, t2)            src/lib.rs:139-145
  *   AffinePoint        64 B = (u, v)                       src/lib.rs:81-84
  *   ExtendedNielsPoint 128 B = (v+u, v-u, z, t2d)          src/lib.rs:327-332
@@ -67,7 +67,8 @@ enum {
     JJ_SUBTRACT = 1u << 3, /* point add entry points compute p - q (src/lib.rs:922-940, 970-988, 1001-1008) */
     JJ_SCALAR_MONT = 1u << 4,
     JJ_OUT_AFFINE = 1u << 5, /* scalar-mul writes normalised AffinePoint (64 B) instead of Extended */
-    JJ_OUT_BYTES = 1u << 6   /* scalar-mul writes the 32-byte encoding (src/lib.rs:455-464)      */
+    JJ_OUT_BYTES = 1u << 6,  /* scalar-mul writes the 32-byte encoding (src/lib.rs:455-464)      */
+    JJ_PRE_ZIP216 = 1u << 7  /* jj_batch_from_bytes: from_bytes_pre_zip216_compatibility (src/lib.rs:485-490) */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -155,6 +156,11 @@ int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* sc
 int32_t jj_batch_normalize(jj_ctx* ctx, const void* in_ext, void* out_affine, size_t n, uint32_t flags);
 /* AffinePoint::to_bytes src/lib.rs:455-464 */
 int32_t jj_affine_to_bytes(jj_ctx* ctx, const void* in_affine, void* out32, size_t n, uint32_t flags);
+/* AffinePoint::batch_from_bytes src/lib.rs:541-627 (per element: from_bytes_inner :492-534): 32-byte
+ * encodings -> AffinePoint; ok[i] = 0 and (0, 0) when v is non-canonical, off the curve, or (ZIP 216) a
+ * non-canonical encoding of (0, +-1).  JJ_PRE_ZIP216 accepts the latter like
+ * from_bytes_pre_zip216_compatibility (:485-490). */
+int32_t jj_batch_from_bytes(jj_ctx* ctx, const void* in32, void* out_affine, uint8_t* ok, size_t n, uint32_t flags);
 /* ExtendedPoint::is_torsion_free src/lib.rs:709-711 ([r]P == identity), is_identity :691-696,
  * is_small_order :699-705; flags_out[i] in {0, 1} */
 int32_t jj_is_torsion_free(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);

@@ -55,6 +55,16 @@ struct FqP {  // [ext] bls12_381::Scalar modulus q; q-1 is at src/lib.rs:1629-16
         constexpr uint32_t t[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
         return t[i];
     }
+    // q - 1 = 2^32 * T with T odd.  (T - 1) / 2 (222 bits, 7 words) and the 2^32-th root of unity
+    // 7^T in Montgomery form ([ext] bls12_381 ROOT_OF_UNITY; SURVEY.md section 8f, recomputed).
+    JJ_CONST_FN uint32_t T_MINUS_1_HALF(int i) {
+        constexpr uint32_t t[8] = {0x7fffffffu, 0x7fff2dffu, 0xa9ded201u, 0x04d0ec02u, 0x199cec04u, 0x94cebea4u, 0x39f6d3a9u, 0u};
+        return t[i];
+    }
+    JJ_CONST_FN uint32_t ROOT_OF_UNITY(int i) {
+        constexpr uint32_t t[8] = {0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u, 0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau};
+        return t[i];
+    }
 };
 struct FrP {  // src/fr.rs:77-82 (MODULUS), :214 (INV), :217-238 (R, R2, R3)
     static constexpr uint32_t M0 = 0xd6f72cb7u, M1 = 0xd0970e5eu, M2 = 0xccc81082u, M3 = 0xa6682093u,
@@ -517,11 +527,9 @@ JJ_DEVICE bool fe_is_canonical(const fe& v) {
     return borrow != 0;
 }
 
-// a^(m-2): 4-bit fixed-window exponentiation over the constant exponent.  The result is
-// the unique inverse (0 for a = 0, flagged by the caller like CtOption, src/fr.rs:539),
-// so the reference's particular addition chain (src/fr.rs:438-538) need not be replayed.
-template <class F>
-JJ_DEVICE void fe_invert(fe& r, const fe& a) {
+// r = a^e for a constant exponent (EXP::word(i), EXP::NW 32-bit words): 4-bit fixed window.
+template <class F, class EXP>
+JJ_DEVICE void fe_pow_const(fe& r, const fe& a) {
     fe tbl[16];
     fe_set_one<F>(tbl[0]);
     tbl[1] = a;
@@ -530,8 +538,8 @@ JJ_DEVICE void fe_invert(fe& r, const fe& a) {
     fe acc;
     fe_set_one<F>(acc);
 #pragma unroll 1
-    for (int wi = 7; wi >= 0; wi--) {
-        uint32_t e = exp_word_m_minus_2<F>(wi);
+    for (int wi = EXP::NW - 1; wi >= 0; wi--) {
+        uint32_t e = EXP::word(wi);
 #pragma unroll 1
         for (int s = 28; s >= 0; s -= 4) {
             mont_sqr<F>(acc, acc);
@@ -543,6 +551,57 @@ JJ_DEVICE void fe_invert(fe& r, const fe& a) {
         }
     }
     r = acc;
+}
+template <class F>
+struct ExpInvert {
+    static constexpr int NW = 8;
+    JJ_CONST_FN uint32_t word(int i) { return F::M_MINUS_2(i); }
+};
+struct ExpFqSqrt {
+    static constexpr int NW = 7;
+    JJ_CONST_FN uint32_t word(int i) { return FqP::T_MINUS_1_HALF(i); }
+};
+// a^(m-2): the result is the unique inverse (0 for a = 0, flagged by the caller like CtOption,
+// src/fr.rs:539), so the reference's particular addition chain (src/fr.rs:438-538) need not be replayed.
+template <class F>
+JJ_DEVICE void fe_invert(fe& r, const fe& a) {
+    fe_pow_const<F, ExpInvert<F>>(r, a);
+}
+// Square root in Fq ([ext] bls12_381::Scalar::sqrt; call sites src/lib.rs:515, :603): Tonelli-Shanks
+// with q - 1 = 2^32 * T.  Returns false for a non-residue.  Which root comes back does not matter to
+// the callers on this path: the sign is fixed from the parity afterwards (src/lib.rs:518-520).
+JJ_DEVICE bool fq_sqrt(fe& r, const fe& a) {
+    if (fe_is_zero(a)) {
+        fe_set_zero(r);
+        return true;
+    }
+    fe w, x, b, z, one;
+    fe_set_one<FqP>(one);
+    fe_pow_const<FqP, ExpFqSqrt>(w, a);  // a^((T-1)/2)
+    mont_mul<FqP>(x, a, w);              // a^((T+1)/2)
+    mont_mul<FqP>(b, x, w);              // a^T
+#pragma unroll
+    for (int i = 0; i < 8; i++) z.w[i] = FqP::ROOT_OF_UNITY(i);
+    int m = 32;
+#pragma unroll 1
+    while (!fe_eq(b, one)) {
+        int i = 0;
+        fe bb = b;
+#pragma unroll 1
+        while (!fe_eq(bb, one)) {
+            mont_sqr<FqP>(bb, bb);
+            if (++i >= m) return false;  // order 2^m: a is a non-residue
+        }
+        fe t = z;
+#pragma unroll 1
+        for (int k = 0; k < m - i - 1; k++) mont_sqr<FqP>(t, t);
+        mont_mul<FqP>(x, x, t);
+        mont_sqr<FqP>(z, t);
+        mont_mul<FqP>(b, b, z);
+        m = i;
+    }
+    r = x;
+    return true;
 }
 
 }  // namespace jj

@@ -148,9 +148,13 @@ const SmulVariant kVariants[] = {
     {64, 3, TABLE_SMEM},       // 8: 3 blocks x 2 warps, shared memory
     {96, 4, TABLE_GMEM},       // 9: 12 warps/SM in 4 blocks
     {64, 6, TABLE_GMEM},       // 10: 12 warps/SM in 6 blocks
+    {384, 1, TABLE_GMEM},      // 11: 12 warps/SM in one block
+    {192, 2, TABLE_GMEM},      // 12: 12 warps/SM in two blocks
+    {512, 1, TABLE_GMEM},      // 13: 16 warps/SM in one block (<= 128 registers)
+    {320, 1, TABLE_GMEM},      // 14: 10 warps/SM
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 5;
+constexpr int kDefaultVariant = 13;
 
 template <int T, int MB, int TAB>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, size_t sc_stride, char* out,
@@ -185,6 +189,10 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(8, 64, 3, TABLE_SMEM);
         V(9, 96, 4, TABLE_GMEM);
         V(10, 64, 6, TABLE_GMEM);
+        V(11, 384, 1, TABLE_GMEM);
+        V(12, 192, 2, TABLE_GMEM);
+        V(13, 512, 1, TABLE_GMEM);
+        V(14, 320, 1, TABLE_GMEM);
     }
 #undef V
     return fail(c, JJ_ERR_INVALID_ARG, "bad scalar-mul variant %d", v);
@@ -708,6 +716,19 @@ int32_t jj_affine_to_bytes(jj_ctx* c, const void* in, void* out, size_t n, uint3
     Out outs[2] = {{out, 32}, {nullptr, 0}};
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) {
         return to_bytes_launch(c, s, din[0], dout[0], cnt);
+    });
+}
+
+int32_t jj_batch_from_bytes(jj_ctx* c, const void* in, void* out, uint8_t* ok, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    In ins[3] = {{in, 32}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{out, 64}, {ok, 1}};
+    bool zip216 = !(flags & JJ_PRE_ZIP216);
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
+        k_from_bytes<<<grid_for(c, cnt, 128, 8), 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], cnt, zip216);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
     });
 }
 

@@ -372,6 +372,23 @@ __global__ void __launch_bounds__(256) k_affine_to_bytes(const char* __restrict_
     }
 }
 
+// AffinePoint::batch_from_bytes (src/lib.rs:541-627): one thread per encoding; the reference's
+// single batched inversion becomes one Fermat inversion per thread (the result is the same field
+// element either way).  ok[i] = 0 and (0, 0) for rejected encodings.
+__global__ void __launch_bounds__(128) k_from_bytes(const char* __restrict__ in, char* __restrict__ out,
+                                                    uint8_t* __restrict__ ok, size_t n, bool zip216) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fe enc;
+        aff_point p;
+        ld_fe(enc, in + i * 32);
+        bool good = point_from_bytes(p, enc, zip216);
+        st_fe(out + i * 64, p.u);
+        st_fe(out + i * 64 + 32, p.v);
+        if (ok) ok[i] = good ? 1 : 0;
+    }
+}
+
 // Integer-multiplier peak probe: register-only, 8 independent accumulate chains per thread of
 // IMAD.WIDE.U32 (32x32+64 -> 64), the instruction the Montgomery kernels are made of and the
 // unit the scalar-mul roofline is counted in.  The multiplicand is the

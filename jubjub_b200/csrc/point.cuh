@@ -43,6 +43,48 @@ struct Curve {
     }
 };
 
+// Fq product / square as used by the point formulas.  On the device they are real (noinline)
+// functions: arguments and result travel in registers (no stack frame), and every point formula
+// shares ONE copy of the 112- / 84-multiplier bodies.  Fully inlined, the scalar-mul loop body is
+// 53 KB of straight-line code, which misses the instruction cache as soon as more than 8 warps per
+// SM run it (ncu: stall_no_instruction 1.7 per issue at 16 warps); with shared bodies the loop is
+// ~15 KB and 12-16 warps/SM keep the multiplier pipe busy.
+#if defined(JJ_HOST_EMUL) || defined(JJ_INLINE_FQ)
+JJ_DEVICE void fq_mul(fe& r, const fe& a, const fe& b) { mont_mul<FqP>(r, a, b); }
+JJ_DEVICE void fq_sqr(fe& r, const fe& a) { mont_sqr<FqP>(r, a); }
+#else
+#if !defined(JJ_FQ_CALL_BY_POINTER)
+static __device__ __noinline__ fe fq_mul_body(fe a, fe b) {
+    fe r;
+    mont_mul<FqP>(r, a, b);
+    return r;
+}
+static __device__ __noinline__ fe fq_sqr_body(fe a) {
+    fe r;
+    mont_sqr<FqP>(r, a);
+    return r;
+}
+JJ_DEVICE void fq_mul(fe& r, const fe& a, const fe& b) { r = fq_mul_body(a, b); }
+JJ_DEVICE void fq_sqr(fe& r, const fe& a) { r = fq_sqr_body(a); }
+#else
+// Operands travel through the thread's local-memory frame (L1-resident, 128-bit LDL/STL on the
+// otherwise idle LSU pipe) instead of ~24 register moves per call: ptxas turns half of such
+// moves into IMAD.MOV on the FMA-heavy pipe, the very pipe the multiplier saturates.
+static __device__ __noinline__ void fq_mul_body(fe* r, const fe* a, const fe* b) {
+    fe x = *a, y = *b, z;
+    mont_mul<FqP>(z, x, y);
+    *r = z;
+}
+static __device__ __noinline__ void fq_sqr_body(fe* r, const fe* a) {
+    fe x = *a, z;
+    mont_sqr<FqP>(z, x);
+    *r = z;
+}
+JJ_DEVICE void fq_mul(fe& r, const fe& a, const fe& b) { fq_mul_body(&r, &a, &b); }
+JJ_DEVICE void fq_sqr(fe& r, const fe& a) { fq_sqr_body(&r, &a); }
+#endif
+#endif
+
 #define JJ_LOAD_CONST(r, ACCESSOR)                          \
     do {                                                   \
         _Pragma("unroll") for (int i_ = 0; i_ < 8; i_++)(r).w[i_] = ACCESSOR(i_); \
@@ -73,9 +115,9 @@ JJ_DEVICE void point_neg(ext_point& r, const ext_point& p) {  // src/lib.rs:196-
 // completed point (u, v, z, t) -> extended (u*t, v*z, z*t, u, v)
 JJ_DEVICE void into_extended(ext_point& r, const fe& cu, const fe& cv, const fe& cz, const fe& ct) {
     fe u, v, z;
-    mont_mul<FqP>(u, cu, ct);
-    mont_mul<FqP>(v, cv, cz);
-    mont_mul<FqP>(z, cz, ct);
+    fq_mul(u, cu, ct);
+    fq_mul(v, cv, cz);
+    fq_mul(z, cz, ct);
     r.t1 = cu;
     r.t2 = cv;
     r.u = u;
@@ -83,19 +125,34 @@ JJ_DEVICE void into_extended(ext_point& r, const fe& cu, const fe& cv, const fe&
     r.z = z;
 }
 
+#if defined(JJ_DOUBLE_INLINE)
+#define JJ_DBL_SQR(r, a) mont_sqr<FqP>(r, a)
+#define JJ_DBL_MUL(r, a, b) mont_mul<FqP>(r, a, b)
+#else
+#define JJ_DBL_SQR(r, a) fq_sqr(r, a)
+#define JJ_DBL_MUL(r, a, b) fq_mul(r, a, b)
+#endif
 JJ_DEVICE void point_double(ext_point& r, const ext_point& p) {
     fe uu, vv, zz2, uv2, vpu, vmu, cu, ct;
-    mont_sqr<FqP>(uu, p.u);
-    mont_sqr<FqP>(vv, p.v);
-    mont_sqr<FqP>(zz2, p.z);
+    JJ_DBL_SQR(uu, p.u);
+    JJ_DBL_SQR(vv, p.v);
+    JJ_DBL_SQR(zz2, p.z);
     fe_dbl<FqP>(zz2, zz2);
     fe_add<FqP>(uv2, p.u, p.v);
-    mont_sqr<FqP>(uv2, uv2);
+    JJ_DBL_SQR(uv2, uv2);
     fe_add<FqP>(vpu, vv, uu);
     fe_sub<FqP>(vmu, vv, uu);
     fe_sub<FqP>(cu, uv2, vpu);
     fe_sub<FqP>(ct, zz2, vmu);
-    into_extended(r, cu, vpu, vmu, ct);
+    fe u, v, z;  // into_extended (src/lib.rs:1052-1060)
+    JJ_DBL_MUL(u, cu, ct);
+    JJ_DBL_MUL(v, vpu, vmu);
+    JJ_DBL_MUL(z, vmu, ct);
+    r.t1 = cu;
+    r.t2 = vpu;
+    r.u = u;
+    r.v = v;
+    r.z = z;
 }
 
 // p + n (sub = false) or p - n (sub = true) for an extended-Niels operand.
@@ -104,12 +161,12 @@ JJ_DEVICE void point_add_niels(ext_point& r, const ext_point& p, const ext_niels
     fe_select(n1, n.vmu, n.vpu, sub);  // multiplies (v - u)
     fe_select(n2, n.vpu, n.vmu, sub);  // multiplies (v + u)
     fe_sub<FqP>(t, p.v, p.u);
-    mont_mul<FqP>(a, t, n1);
+    fq_mul(a, t, n1);
     fe_add<FqP>(t, p.v, p.u);
-    mont_mul<FqP>(b, t, n2);
-    mont_mul<FqP>(c, p.t1, p.t2);
-    mont_mul<FqP>(c, c, n.t2d);
-    mont_mul<FqP>(d, p.z, n.z);
+    fq_mul(b, t, n2);
+    fq_mul(c, p.t1, p.t2);
+    fq_mul(c, c, n.t2d);
+    fq_mul(d, p.z, n.z);
     fe_dbl<FqP>(d, d);
     fe cu, cv, dpc, dmc, cz, ct;
     fe_sub<FqP>(cu, b, a);
@@ -126,11 +183,11 @@ JJ_DEVICE void point_add_aff_niels(ext_point& r, const ext_point& p, const aff_n
     fe_select(n1, n.vmu, n.vpu, sub);
     fe_select(n2, n.vpu, n.vmu, sub);
     fe_sub<FqP>(t, p.v, p.u);
-    mont_mul<FqP>(a, t, n1);
+    fq_mul(a, t, n1);
     fe_add<FqP>(t, p.v, p.u);
-    mont_mul<FqP>(b, t, n2);
-    mont_mul<FqP>(c, p.t1, p.t2);
-    mont_mul<FqP>(c, c, n.t2d);
+    fq_mul(b, t, n2);
+    fq_mul(c, p.t1, p.t2);
+    fq_mul(c, c, n.t2d);
     fe_dbl<FqP>(d, p.z);
     fe cu, cv, dpc, dmc, cz, ct;
     fe_sub<FqP>(cu, b, a);
@@ -148,22 +205,54 @@ JJ_DEVICE void point_to_niels(ext_niels& n, const ext_point& p) {
     fe_add<FqP>(n.vpu, p.v, p.u);
     fe_sub<FqP>(n.vmu, p.v, p.u);
     n.z = p.z;
-    mont_mul<FqP>(t, p.t1, p.t2);
-    mont_mul<FqP>(n.t2d, t, d2);
+    fq_mul(t, p.t1, p.t2);
+    fq_mul(n.t2d, t, d2);
 }
 JJ_DEVICE void affine_to_niels(aff_niels& n, const aff_point& p) {
     fe d2, t;
     JJ_LOAD_CONST(d2, Curve::D2);
     fe_add<FqP>(n.vpu, p.v, p.u);
     fe_sub<FqP>(n.vmu, p.v, p.u);
-    mont_mul<FqP>(t, p.u, p.v);
-    mont_mul<FqP>(n.t2d, t, d2);
+    fq_mul(t, p.u, p.v);
+    fq_mul(n.t2d, t, d2);
 }
 // p + q with both extended: q.to_niels() then the 8M add (src/lib.rs:992-999).
 JJ_DEVICE void point_add(ext_point& r, const ext_point& p, const ext_point& q, bool sub) {
     ext_niels n;
     point_to_niels(n, q);
     point_add_niels(r, p, n, sub);
+}
+// AffinePoint::from_bytes_inner (src/lib.rs:492-534) for one encoding held as 8 LE words.
+// Returns false (and leaves the zero point) for non-canonical v, off-curve v, or -- with zip216 --
+// the non-canonical encodings of (0, +-1) whose sign bit is set (ZIP 216, src/lib.rs:527-531).
+JJ_DEVICE bool point_from_bytes(aff_point& p, const fe& enc, bool zip216) {
+    fe vraw = enc, v, v2, num, den, inv, u2, u, un, uc, one, d;
+    uint32_t sign = vraw.w[7] >> 31;
+    vraw.w[7] &= 0x7fffffffu;
+    fe_set_zero(p.u);
+    fe_set_zero(p.v);
+    if (!fe_is_canonical<FqP>(vraw)) return false;
+    fe_from_raw<FqP>(v, vraw);
+    fe_set_one<FqP>(one);
+    JJ_LOAD_CONST(d, Curve::D);
+    fq_sqr(v2, v);
+    fe_sub<FqP>(num, v2, one);          // v^2 - 1
+    fq_mul(den, d, v2);
+    fe_add<FqP>(den, one, den);         // 1 + d v^2 (never zero: -1/d is a non-residue)
+    fe_invert<FqP>(inv, den);
+    fq_mul(u2, num, inv);
+    if (!fq_sqrt(u, u2)) return false;
+    fe_to_canonical<FqP>(uc, u);
+    bool flip = ((uc.w[0] ^ sign) & 1u) != 0;
+    fe_neg<FqP>(un, u);
+    fe_select(p.u, u, un, flip);
+    p.v = v;
+    if (zip216 && fe_is_zero(u) && flip) {
+        fe_set_zero(p.u);
+        fe_set_zero(p.v);
+        return false;
+    }
+    return true;
 }
 JJ_DEVICE bool point_is_identity(const ext_point& p) {  // u == 0 and v == z  src/lib.rs:691-696
     return fe_is_zero(p.u) && fe_eq(p.v, p.z);

@@ -227,6 +227,11 @@ class Engine:
     def affine_to_bytes(self, a, out=None):
         return self._call("jj_affine_to_bytes", [(a, AFF_W, np.uint64)], 32, np.uint8, out=out)
 
+    def batch_from_bytes(self, enc, zip216=True):
+        """AffinePoint::batch_from_bytes (src/lib.rs:541-627) -> (points, ok)."""
+        return self._call("jj_batch_from_bytes", [(enc, 32, np.uint8)], AFF_W, ok=True,
+                          flags=0 if zip216 else L.JJ_PRE_ZIP216)
+
     def _flag(self, name, p):
         o = self._call(name, [(p, EXT_W, np.uint64)], 1, np.uint8)
         return o if isinstance(o, DeviceArray) else o.reshape(-1)

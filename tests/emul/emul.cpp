@@ -98,3 +98,19 @@ extern "C" void emul_scalar_mul_fixed(const uint32_t* table, const void* k_, voi
         ((ext_point*)out_)[i] = acc;
     }
 }
+
+extern "C" void emul_from_bytes(const void* in32, void* out_affine, uint8_t* ok, int zip216, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        aff_point p;
+        ok[i] = point_from_bytes(p, ((const fe*)in32)[i], zip216 != 0) ? 1 : 0;
+        ((aff_point*)out_affine)[i] = p;
+    }
+}
+extern "C" void emul_fq_sqrt(const void* a, void* out, uint8_t* ok, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fe r;
+        fe_set_zero(r);
+        ok[i] = fq_sqrt(r, ((const fe*)a)[i]) ? 1 : 0;
+        ((fe*)out)[i] = r;
+    }
+}

@@ -170,7 +170,7 @@ def _smul_case(oracle, n):
     return p, k
 
 
-@pytest.mark.parametrize("variant", list(range(0, 11)))
+@pytest.mark.parametrize("variant", list(range(0, 15)))
 def test_scalar_mul_variants(eng, oracle, variant):
     eng.set_scalar_mul_variant(variant)
     try:
@@ -268,6 +268,36 @@ def test_batch_normalize_and_flags(eng, oracle):
     g8 = oracle.ext_mul_by_cofactor(p[9:30])
     assert eng.is_torsion_free(g8).all()
     assert (eng.is_small_order(p[:40]) == oracle.is_small_order(p[:40])).all()
+
+
+def test_batch_from_bytes(eng, oracle):
+    """src/lib.rs:541-627, KATs :1811-1876 and ZIP 216 :1894-1935."""
+    p = _points(oracle, 900)
+    enc = oracle.affine_to_bytes(oracle.batch_normalize(oracle.ext_double(p)))
+    bad = enc[:200].copy()
+    bad[:, 0] ^= 1
+    extra = b32(*K.SERIALIZED_MULTIPLES_OF_8G, *K.ZIP216_NON_CANONICAL, [0xFF] * 32, [1] + [0] * 31, [0] * 32)
+    allenc = np.concatenate([enc, bad, extra])
+    want, wok = oracle.batch_from_bytes(allenc)
+    got, ok = eng.batch_from_bytes(allenc)
+    assert (ok == wok).all() and 0 < ok.sum() < len(ok)
+    assert (got == want).all()  # rejected encodings come back as (0, 0) on both sides
+    g8 = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator()))
+    cur = g8
+    base = len(enc) + len(bad)
+    for i in range(16):  # the reference test: batch-decoded k*(8G) equals the point itself
+        assert ok[base + i] == 1 and (got[base + i] == oracle.ext_to_affine(cur)[0]).all()
+        cur = oracle.ext_add(cur, g8)
+    z = base + 16
+    assert ok[z] == 0 and ok[z + 1] == 0  # ZIP 216: non-canonical (0, 1) and (0, -1) rejected ...
+    got2, ok2 = eng.batch_from_bytes(allenc, zip216=False)
+    want2, wok2 = oracle.affine_from_bytes(allenc, zip216=False)
+    assert ok2[z] == 1 and ok2[z + 1] == 1 and (ok2 == wok2).all()  # ... and accepted by the pre-ZIP-216 API
+    assert (got2[ok2 == 1] == want2[wok2 == 1]).all()
+    # round trip on the device: decode(encode(P)) == P
+    aff = eng.batch_normalize(p)
+    back, okb = eng.batch_from_bytes(eng.affine_to_bytes(aff))
+    assert okb.all() and (back == aff).all()
 
 
 def test_find_eight_torsion_on_gpu(eng, oracle):

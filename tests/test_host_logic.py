@@ -139,3 +139,29 @@ def test_emulated_points_and_scalar_mul(emul, oracle):
     assert (oracle.batch_normalize(got) == oracle.batch_normalize(want)).all()
     got = emul.smul_fixed(oracle.generator(), k)
     assert (oracle.batch_normalize(got) == oracle.batch_normalize(oracle.scalar_mul_fixed(oracle.generator(), k))).all()
+
+
+def test_emulated_sqrt_and_decode(built, oracle):
+    from tests.golden import reference_kats as K
+
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libjj_emul.so"))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    a = oracle.fe_stream(FQ, 77, 300)
+    a[0] = 0
+    out, ok = np.zeros_like(a), np.zeros(len(a), np.uint8)
+    lib.emul_fq_sqrt(P(a), P(out), P(ok), C.c_size_t(len(a)))
+    assert (ok == oracle.fe_sqrt(FQ, a)[1]).all()
+    assert (oracle.fe_batch(FQ, oracle.OP_SQUARE, out[ok == 1]) == a[ok == 1]).all()
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 5, 120))
+    enc = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(np.repeat(g, 120, axis=0), t)))
+    bad = enc[:40].copy()
+    bad[:, 0] ^= 1
+    extra = np.array(K.SERIALIZED_MULTIPLES_OF_8G + K.ZIP216_NON_CANONICAL + [[0xFF] * 32, [1] + [0] * 31, [0] * 32],
+                     dtype=np.uint8)
+    allenc = np.concatenate([enc, bad, extra])
+    for zip216 in (1, 0):
+        got, ok = np.zeros((len(allenc), 8), np.uint64), np.zeros(len(allenc), np.uint8)
+        lib.emul_from_bytes(P(allenc), P(got), P(ok), zip216, C.c_size_t(len(allenc)))
+        want, wok = oracle.affine_from_bytes(allenc, zip216=bool(zip216))
+        assert (ok == wok).all() and (got[ok == 1] == want[wok == 1]).all()
