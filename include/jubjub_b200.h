@@ -179,6 +179,17 @@ int32_t jj_comm_destroy(jj_ctx* ctx);
 int32_t jj_scalar_mul_sharded(jj_ctx* ctx, const void* points_ext_local, const void* scalars32_local,
                               void* out_all, size_t n_local, uint32_t flags);
 
+/* Fused compute + all-gather over NVLink peer memory.  Each rank exports its gathered-output buffer
+ * (jj_ipc_export -> 64-byte cudaIpcMemHandle), the host exchanges the handles, every rank opens its
+ * peers' buffers (jj_ipc_open) and registers the nranks pointers in rank order (own pointer at index
+ * rank).  jj_scalar_mul_sharded with ExtendedPoint output then stores every result straight into all
+ * ranks' buffers from the scalar-mul kernel's epilogue (P2P stores) and ends with a 4-byte
+ * stream-ordered NCCL rendezvous instead of a separate ncclAllGather. */
+int32_t jj_ipc_export(jj_ctx* ctx, const void* dptr, void* handle64);
+int32_t jj_ipc_open(jj_ctx* ctx, const void* handle64, void** dptr);
+int32_t jj_ipc_close(jj_ctx* ctx, void* dptr);
+int32_t jj_comm_set_peer_outputs(jj_ctx* ctx, void* const* peer_out_all, int32_t count);
+
 #ifdef __cplusplus
 }
 #endif

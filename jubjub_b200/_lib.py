@@ -56,6 +56,8 @@ PROTOTYPES = {
     "jj_is_torsion_free": _UNARY, "jj_is_identity": _UNARY, "jj_is_small_order": _UNARY,
     "jj_comm_init": [_i32, _i32, _vp], "jj_comm_destroy": [],
     "jj_scalar_mul_sharded": [_vp, _vp, _vp, _sz, _u32],
+    "jj_ipc_export": [_vp, _vp], "jj_ipc_open": [_vp, C.POINTER(_vp)], "jj_ipc_close": [_vp],
+    "jj_comm_set_peer_outputs": [C.POINTER(_vp), _i32],
 }
 # entry points without a leading ctx / with another return type
 _SPECIAL = {

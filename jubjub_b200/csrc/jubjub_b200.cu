@@ -45,6 +45,7 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -59,6 +60,7 @@ bool load_nccl() {
         g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
         g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
         g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+        g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
         g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
         g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
         if (g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy) {
@@ -93,6 +95,8 @@ struct jj_ctx {
     size_t flush_bytes = 0;
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    PeerOut peers{};  // peer-mapped gathered-output buffers (fused all-gather); n_peers = 0: off
+    int* barrier_word = nullptr;
     uint64_t launches = 0;
     char err[512];
 };
@@ -157,27 +161,51 @@ constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
 
 template <int T, int MB, int TAB>
-int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, size_t sc_stride, char* out,
-                      uint8_t* flag_out, size_t n, char** tbl, size_t* tbl_cap, bool scalar_mont) {
+int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
     auto kern = k_scalar_mul<T, MB, TAB>;
     size_t smem = TAB == TABLE_SMEM ? (size_t)(T / 32) * 32768 : 0;
-    int grid = grid_for(c, n, T, MB);
+    int grid = grid_for(c, a.n, T, MB);
     if (TAB == TABLE_SMEM) {
         CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
         int32_t rc = ensure(c, tbl, tbl_cap, (size_t)grid * (T / 32) * 32768);
         if (rc) return rc;
     }
-    kern<<<grid, T, smem, s>>>(pts, sc, sc_stride, out, flag_out, n, *tbl, scalar_mont);
+    a.tbl_scratch = *tbl;
+    kern<<<grid, T, smem, s>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return JJ_OK;
+}
+template <int T, int MB>
+int32_t launch_smul_slots(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
+    auto kern = k_scalar_mul_slots<T, MB>;
+    size_t smem = (size_t)(T / 32) * S_COUNT * 1024;
+    int grid = grid_for(c, a.n, T, MB);
+    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int32_t rc = ensure(c, tbl, tbl_cap, (size_t)grid * (T / 32) * 32768);
+    if (rc) return rc;
+    a.tbl_scratch = *tbl;
+    kern<<<grid, T, smem, s>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
     return JJ_OK;
 }
 int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, size_t sc_stride, char* out,
-                    uint8_t* flag_out, size_t n, char** tbl, size_t* tbl_cap, bool scalar_mont) {
+                    uint8_t* flag_out, size_t n, char** tbl, size_t* tbl_cap, bool scalar_mont,
+                    const PeerOut* peers = nullptr) {
     int v = c->smul_variant > 0 && c->smul_variant < kNumVariants ? c->smul_variant : kDefaultVariant;
+    SmulArgs a{};
+    a.points = pts;
+    a.scalars = sc;
+    a.scalar_stride = sc_stride;
+    a.out = out;
+    a.flag_out = flag_out;
+    a.n = n;
+    a.scalar_mont = scalar_mont;
+    if (peers) a.peers = *peers;
 #define V(ID, T, MB, TAB) \
-    case ID: return launch_smul_t<T, MB, TAB>(c, s, pts, sc, sc_stride, out, flag_out, n, tbl, tbl_cap, scalar_mont)
+    case ID: return launch_smul_t<T, MB, TAB>(c, s, a, tbl, tbl_cap)
     switch (v) {
         V(1, 224, 1, TABLE_SMEM);
         V(2, 128, 2, TABLE_GMEM);
@@ -193,6 +221,10 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(12, 192, 2, TABLE_GMEM);
         V(13, 512, 1, TABLE_GMEM);
         V(14, 320, 1, TABLE_GMEM);
+        case 15: return launch_smul_slots<512, 1>(c, s, a, tbl, tbl_cap);
+        case 16: return launch_smul_slots<384, 1>(c, s, a, tbl, tbl_cap);
+        case 17: return launch_smul_slots<544, 1>(c, s, a, tbl, tbl_cap);
+        case 18: return launch_smul_slots<256, 2>(c, s, a, tbl, tbl_cap);
     }
 #undef V
     return fail(c, JJ_ERR_INVALID_ARG, "bad scalar-mul variant %d", v);
@@ -417,6 +449,7 @@ int32_t jj_destroy(jj_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    if (c->barrier_word) cudaFree(c->barrier_word);
     for (int k = 0; k < kStages; k++) {
         for (char* b : c->st[k].buf)
             if (b) cudaFree(b);
@@ -798,17 +831,75 @@ int32_t jj_scalar_mul_sharded(jj_ctx* c, const void* points_local, const void* s
                               size_t n_local, uint32_t flags) {
     if (!c || !out_all) return JJ_ERR_INVALID_ARG;
     if (!(flags & JJ_DEVICE_PTRS)) return fail(c, JJ_ERR_INVALID_ARG, "jj_scalar_mul_sharded takes device pointers");
+    CU(c, cudaSetDevice(c->device));
     size_t unit = out_unit(flags);
-    char* mine = (char*)out_all + (size_t)c->rank * n_local * unit;
-    int32_t rc = jj_scalar_mul(c, points_local, scalars_local, mine, n_local, flags | JJ_ASYNC);
-    if (rc) return rc;
-    if (c->nranks > 1) {
-        if (!c->nccl_comm) return fail(c, JJ_ERR_NCCL, "jj_comm_init was not called");
-        // in-place all-gather: every rank's block already sits at its own offset (ncclUint8 = 1... char)
-        int nrc = g_nccl.AllGather(mine, out_all, n_local * unit, /*ncclInt8*/ 0, c->nccl_comm, c->stream);
-        if (nrc != 0) return fail(c, JJ_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+    bool fused = c->peers.n_peers == c->nranks && c->nranks > 1 && unit == 160;
+    if (fused) {
+        // compute + all-gather in ONE kernel: results are stored into every rank's gathered buffer
+        if (c->peers.ptr[c->rank] != (char*)out_all) return fail(c, JJ_ERR_INVALID_ARG, "out_all is not the registered peer buffer");
+        if (((uintptr_t)points_local | (uintptr_t)scalars_local | (uintptr_t)out_all) & 31)
+            return fail(c, JJ_ERR_INVALID_ARG, "device pointer not 32-byte aligned");
+        PeerOut po = c->peers;
+        po.base_unit = (size_t)c->rank * n_local;
+        int32_t rc = launch_smul(c, c->stream, (const char*)points_local, (const char*)scalars_local, 32, nullptr, nullptr,
+                                 n_local, &c->tbl, &c->tbl_cap, flags & JJ_SCALAR_MONT, &po);
+        if (rc) return rc;
+        // stream-ordered rendezvous: once this 4-byte all-reduce completes here, every peer's kernel
+        // (enqueued before its own all-reduce) has finished storing into this rank's buffer
+        if (!c->barrier_word) {
+            CU(c, cudaMalloc((void**)&c->barrier_word, 256));
+            CU(c, cudaMemset(c->barrier_word, 0, 256));
+        }
+        int nrc = g_nccl.AllReduce(c->barrier_word, c->barrier_word + 32, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+        if (nrc != 0) return fail(c, JJ_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+    } else {
+        char* mine = (char*)out_all + (size_t)c->rank * n_local * unit;
+        int32_t rc = jj_scalar_mul(c, points_local, scalars_local, mine, n_local, flags | JJ_ASYNC);
+        if (rc) return rc;
+        if (c->nranks > 1) {
+            if (!c->nccl_comm) return fail(c, JJ_ERR_NCCL, "jj_comm_init was not called");
+            // in-place all-gather: every rank's block already sits at its own offset
+            int nrc = g_nccl.AllGather(mine, out_all, n_local * unit, /*ncclInt8*/ 0, c->nccl_comm, c->stream);
+            if (nrc != 0) return fail(c, JJ_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+        }
     }
     if (!(flags & JJ_ASYNC)) CU(c, cudaStreamSynchronize(c->stream));
+    return JJ_OK;
+}
+
+int32_t jj_ipc_export(jj_ctx* c, const void* dptr, void* handle64) {
+    if (!c || !dptr || !handle64) return JJ_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, (void*)dptr));
+    return JJ_OK;
+}
+int32_t jj_ipc_open(jj_ctx* c, const void* handle64, void** dptr) {
+    if (!c || !dptr || !handle64) return JJ_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return JJ_OK;
+}
+int32_t jj_ipc_close(jj_ctx* c, void* dptr) {
+    if (!c || !dptr) return JJ_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaIpcCloseMemHandle(dptr));
+    return JJ_OK;
+}
+int32_t jj_comm_set_peer_outputs(jj_ctx* c, void* const* peer_out_all, int32_t count) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (!peer_out_all || count == 0) {
+        c->peers.n_peers = 0;
+        return JJ_OK;
+    }
+    if (count != c->nranks || count > 8) return fail(c, JJ_ERR_INVALID_ARG, "need one pointer per rank (<= 8)");
+    for (int r = 0; r < count; r++) {
+        if (!peer_out_all[r] || ((uintptr_t)peer_out_all[r] & 31)) return fail(c, JJ_ERR_INVALID_ARG, "bad peer pointer");
+        c->peers.ptr[r] = (char*)peer_out_all[r];
+    }
+    c->peers.n_peers = count;
     return JJ_OK;
 }
 

@@ -9,7 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "scalarmul.cuh"
+#include "slotmul.cuh"
 
 namespace jj {
 
@@ -236,30 +236,83 @@ struct GmemTable {
 
 enum { TABLE_SMEM = 0, TABLE_GMEM = 1 };
 
+// Fused all-gather: when n_peers > 0 every result is stored straight into each peer GPU's copy of
+// the gathered output (peer-mapped pointers, NVLink P2P stores) at unit offset `base_unit + i`,
+// instead of into `out`.  The collective rides the compute kernel's epilogue; no separate gather.
+struct PeerOut {
+    char* ptr[8];
+    int n_peers;
+    size_t base_unit;
+};
+struct SmulArgs {
+    const char* points;
+    const char* scalars;
+    size_t scalar_stride;
+    char* out;
+    uint8_t* flag_out;
+    size_t n;
+    char* tbl_scratch;
+    bool scalar_mont;
+    PeerOut peers;
+};
+__device__ __forceinline__ void smul_store(const SmulArgs& a, size_t i, const ext_point& acc) {
+    if (a.peers.n_peers > 0) {
+#pragma unroll 1
+        for (int r = 0; r < a.peers.n_peers; r++) st_ext(a.peers.ptr[r], a.peers.base_unit + i, acc);
+    } else {
+        st_ext(a.out, i, acc);
+    }
+}
+
 template <int THREADS, int MIN_BLOCKS, int TABLE>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-    k_scalar_mul(const char* __restrict__ points, const char* __restrict__ scalars, size_t scalar_stride,
-                 char* __restrict__ out, uint8_t* __restrict__ flag_out, size_t n, char* __restrict__ tbl_scratch,
-                 bool scalar_mont) {
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulArgs a) {
     extern __shared__ uint4 smem_tbl[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t stride = (size_t)gridDim.x * THREADS;
-    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < a.n; i += stride) {
         ext_point P, acc;
         fe k;
-        ld_ext(P, points, i);
-        ld_fe(k, scalars + i * scalar_stride);
-        if (scalar_mont) fe_to_canonical<FrP>(k, k);  // Fr::to_bytes, src/lib.rs:877
+        ld_ext(P, a.points, i);
+        ld_fe(k, a.scalars + i * a.scalar_stride);
+        if (a.scalar_mont) fe_to_canonical<FrP>(k, k);  // Fr::to_bytes, src/lib.rs:877
         if (TABLE == TABLE_SMEM) {
             SmemTable t{smem_tbl + (size_t)warp * 2048 + lane};
             scalar_mul_core(acc, P, k.w, t);
         } else {
             size_t gwarp = (size_t)blockIdx.x * (THREADS / 32) + warp;
-            GmemTable t{tbl_scratch + gwarp * 32768 + lane * 32};
+            GmemTable t{a.tbl_scratch + gwarp * 32768 + lane * 32};
             scalar_mul_core(acc, P, k.w, t);
         }
-        if (flag_out) flag_out[i] = point_is_identity(acc) ? 1 : 0;  // is_torsion_free
-        else st_ext(out, i, acc);
+        if (a.flag_out) a.flag_out[i] = point_is_identity(acc) ? 1 : 0;  // is_torsion_free
+        else smul_store(a, i, acc);
+    }
+}
+
+// Slot-file mapping (slotmul.cuh): the working set of each thread lives in 13 shared-memory slots
+// (13 KB per warp), field operations are shared noinline routines.  Window table in global scratch.
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul_slots(const SmulArgs a) {
+    extern __shared__ uint4 smem_slots[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SlotFile S{(uint32_t)__cvta_generic_to_shared(smem_slots) + (uint32_t)warp * (S_COUNT * 1024u) + (uint32_t)lane * 16u};
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    const size_t gwarp = (size_t)blockIdx.x * (THREADS / 32) + warp;
+    GmemTable t{a.tbl_scratch + gwarp * 32768 + lane * 32};
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < a.n; i += stride) {
+        fe k, f;
+        const char* b = a.points + i * 160;
+        ld_fe(f, b);       S.st(S_U, f);
+        ld_fe(f, b + 32);  S.st(S_V, f);
+        ld_fe(f, b + 64);  S.st(S_Z, f);
+        ld_fe(f, b + 96);  S.st(S_T1, f);
+        ld_fe(f, b + 128); S.st(S_T2, f);
+        ld_fe(k, a.scalars + i * a.scalar_stride);
+        if (a.scalar_mont) fe_to_canonical<FrP>(k, k);
+        scalar_mul_slots(S, k.w, t);
+        ext_point acc;
+        S.ld(acc.u, S_U); S.ld(acc.v, S_V); S.ld(acc.z, S_Z); S.ld(acc.t1, S_T1); S.ld(acc.t2, S_T2);
+        if (a.flag_out) a.flag_out[i] = point_is_identity(acc) ? 1 : 0;
+        else smul_store(a, i, acc);
     }
 }
 

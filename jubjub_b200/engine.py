@@ -288,6 +288,29 @@ class Engine:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         self._check(self.lib.jj_comm_init(self.ctx, nranks, rank, buf))
 
+    def ipc_export(self, darr):
+        """64-byte CUDA IPC handle of a DeviceArray (to be sent to the peer processes)."""
+        buf = (C.c_char * 64)()
+        self._check(self.lib.jj_ipc_export(self.ctx, darr.ptr, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._check(self.lib.jj_ipc_open(self.ctx, (C.c_char * 64).from_buffer_copy(handle), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self.lib.jj_ipc_close(self.ctx, ptr))
+
+    def set_peer_outputs(self, ptrs):
+        """Register every rank's gathered-output buffer (rank order; own buffer at index rank) to fuse
+        the all-gather into the scalar-mul kernel (P2P stores over NVLink).  None / [] switches back."""
+        if not ptrs:
+            self._check(self.lib.jj_comm_set_peer_outputs(self.ctx, None, 0))
+            return
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._check(self.lib.jj_comm_set_peer_outputs(self.ctx, arr, len(ptrs)))
+
     def scalar_mul_sharded(self, points_local, scalars_local, out_all, output="extended", async_=False):
         """This rank's shard + all-gather of every rank's results into out_all (device)."""
         w, dt, f = self._out_fmt(output)

@@ -34,7 +34,7 @@ extern "C" void emul_fe_op(int which, int op, const void* a, const void* b, void
     else fe_op<FrP>(op, (const fe*)a, (const fe*)b, (fe*)out, n);
 }
 
-#include "../../jubjub_b200/csrc/scalarmul.cuh"
+#include "../../jubjub_b200/csrc/slotmul.cuh"
 
 // op: 0 double, 1 add (ext+ext), 2 sub (ext-ext), 3 add ext-niels, 4 sub ext-niels,
 //     5 add affine-niels, 6 sub affine-niels, 7 to_niels (ext), 8 to_niels (affine), 9 neg
@@ -112,5 +112,19 @@ extern "C" void emul_fq_sqrt(const void* a, void* out, uint8_t* ok, size_t n) {
         fe_set_zero(r);
         ok[i] = fq_sqrt(r, ((const fe*)a)[i]) ? 1 : 0;
         ((fe*)out)[i] = r;
+    }
+}
+
+extern "C" void emul_scalar_mul_slots(const void* p_, const void* k_, void* out_, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t slots[S_COUNT * 8];
+        SlotFile S{slots};
+        const ext_point& P = ((const ext_point*)p_)[i];
+        S.st(S_U, P.u); S.st(S_V, P.v); S.st(S_Z, P.z); S.st(S_T1, P.t1); S.st(S_T2, P.t2);
+        LocalTable tbl;
+        scalar_mul_slots(S, ((const uint32_t*)k_) + 8 * i, tbl);
+        ext_point r;
+        S.ld(r.u, S_U); S.ld(r.v, S_V); S.ld(r.z, S_Z); S.ld(r.t1, S_T1); S.ld(r.t2, S_T2);
+        ((ext_point*)out_)[i] = r;
     }
 }

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, uid_q, n_local, ret):
+def _worker(rank, world, uid_q, n_local, ret, handles, barrier):
     sys.path.insert(0, ROOT)
     import jubjub_b200 as jj
     from oracle import binding as ob
@@ -34,6 +34,20 @@ def _worker(rank, world, uid_q, n_local, ret):
         out_all = eng.empty((world * n_local, width), dtype)
         eng.scalar_mul_sharded(eng.to_device(pts), eng.to_device(k), out_all, output=output)
         ret[(rank, output)] = out_all.download()
+    # fused path: P2P stores into every rank's buffer from the kernel epilogue, no ncclAllGather
+    out_all = eng.empty((world * n_local, 20), np.uint64)
+    handles[rank] = eng.ipc_export(out_all)
+    barrier.wait()
+    ptrs = [out_all.ptr if r == rank else eng.ipc_open(handles[r]) for r in range(world)]
+    eng.set_peer_outputs(ptrs)
+    eng.scalar_mul_sharded(eng.to_device(pts), eng.to_device(k), out_all, output="extended")
+    ret[(rank, "fused")] = out_all.download()
+    barrier.wait()  # nobody frees a buffer a peer may still be writing or reading
+    eng.set_peer_outputs(None)
+    for r in range(world):
+        if r != rank:
+            eng.ipc_close(ptrs[r])
+    barrier.wait()
     eng.close()
 
 
@@ -46,8 +60,8 @@ def test_sharded_all_gather_2gpu(oracle):
     world, n_local = 2, 3000
     ctx = mp.get_context("spawn")
     mgr = ctx.Manager()
-    ret, q = mgr.dict(), mgr.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, q, n_local, ret)) for r in range(world)]
+    ret, q, handles, barrier = mgr.dict(), mgr.Queue(), mgr.dict(), mgr.Barrier(world)
+    procs = [ctx.Process(target=_worker, args=(r, world, q, n_local, ret, handles, barrier)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -61,3 +75,4 @@ def test_sharded_all_gather_2gpu(oracle):
     for r in range(world):
         assert (oracle.batch_normalize(ret[(r, "extended")]) == want_aff).all()
         assert (ret[(r, "bytes")] == oracle.affine_to_bytes(want_aff)).all()
+        assert (ret[(r, "fused")] == ret[(r, "extended")]).all()  # same kernel, same bits, gathered by P2P stores
