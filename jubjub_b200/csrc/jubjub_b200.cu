@@ -98,6 +98,7 @@ struct jj_ctx {
     PeerOut peers{};  // peer-mapped gathered-output buffers (fused all-gather); n_peers = 0: off
     int* barrier_word = nullptr;
     uint64_t launches = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;
     char err[512];
 };
 
@@ -156,9 +157,30 @@ const SmulVariant kVariants[] = {
     {192, 2, TABLE_GMEM},      // 12: 12 warps/SM in two blocks
     {512, 1, TABLE_GMEM},      // 13: 16 warps/SM in one block (<= 128 registers)
     {320, 1, TABLE_GMEM},      // 14: 10 warps/SM
+    {512, 1, 2},               // 15: slot-file mapping (slotmul.cuh), 16 warps/SM
+    {384, 1, 2},               // 16: slot-file, 12 warps/SM
+    {544, 1, 2},               // 17: slot-file, 17 warps/SM (226 KB of shared memory)
+    {256, 2, 2},               // 18: slot-file, 2 x 8 warps/SM
+    {448, 1, TABLE_GMEM},      // 19: 14 warps/SM (<= 146 registers)
+    {480, 1, TABLE_GMEM},      // 20: 15 warps/SM (<= 136 registers)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
+
+// Keep the window-table scratch resident in L2 (persisting access-policy window on the launch
+// stream): it is rewritten by every scalar-mul, and without the hint the streaming inputs/outputs
+// evict it, turning ~1 KB of table stores per unit into DRAM write-backs (ncu: 3.5x the
+// algorithmic traffic).
+void pin_table_in_l2(jj_ctx* c, cudaStream_t s, char* tbl, size_t bytes) {
+    if (!c->l2_persist_max || !tbl) return;
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = tbl;
+    v.accessPolicyWindow.num_bytes = std::min(bytes, c->l2_window_max);
+    v.accessPolicyWindow.hitRatio = bytes <= c->l2_persist_max ? 1.0f : (float)c->l2_persist_max / (float)bytes;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);  // best effort
+}
 
 template <int T, int MB, int TAB>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
@@ -170,6 +192,7 @@ int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t*
     } else {
         int32_t rc = ensure(c, tbl, tbl_cap, (size_t)grid * (T / 32) * 32768);
         if (rc) return rc;
+        pin_table_in_l2(c, s, *tbl, (size_t)grid * (T / 32) * 32768);
     }
     a.tbl_scratch = *tbl;
     kern<<<grid, T, smem, s>>>(a);
@@ -185,6 +208,7 @@ int32_t launch_smul_slots(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, siz
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int32_t rc = ensure(c, tbl, tbl_cap, (size_t)grid * (T / 32) * 32768);
     if (rc) return rc;
+    pin_table_in_l2(c, s, *tbl, (size_t)grid * (T / 32) * 32768);
     a.tbl_scratch = *tbl;
     kern<<<grid, T, smem, s>>>(a);
     c->launches++;
@@ -221,6 +245,8 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(12, 192, 2, TABLE_GMEM);
         V(13, 512, 1, TABLE_GMEM);
         V(14, 320, 1, TABLE_GMEM);
+        V(19, 448, 1, TABLE_GMEM);
+        V(20, 480, 1, TABLE_GMEM);
         case 15: return launch_smul_slots<512, 1>(c, s, a, tbl, tbl_cap);
         case 16: return launch_smul_slots<384, 1>(c, s, a, tbl, tbl_cap);
         case 17: return launch_smul_slots<544, 1>(c, s, a, tbl, tbl_cap);
@@ -357,10 +383,13 @@ int32_t pt_binary(jj_ctx* c, const void* p, size_t pu, const void* q, size_t qu,
 }
 
 int32_t normalize_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, size_t n) {
-    // ~32 points per thread's inversion chain, at least one full wave of 128-thread blocks
-    size_t threads_total = std::max<size_t>((n + 31) / 32, std::min<size_t>(n, (size_t)c->sm_count * 128));
-    int grid = (int)((threads_total + 127) / 128);
-    k_batch_normalize<<<grid, 128, 0, s>>>(in, out, n);
+    // one Fermat inversion per thread amortised over its strided chain: ~32 points per thread for
+    // large batches, grid sized in whole multiples of the SM count (2 x 128-thread blocks each)
+    size_t blocks = (n + 128 * 32 - 1) / (128 * 32);
+    size_t per_wave = (size_t)c->sm_count * 2;
+    blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
+    blocks = std::min(blocks, (n + 127) / 128);
+    k_batch_normalize<<<(int)blocks, 128, 0, s>>>(in, out, n);
     c->launches++;
     CU(c, cudaGetLastError());
     return JJ_OK;
@@ -433,6 +462,11 @@ int32_t jj_init(int device, jj_ctx** out) {
         return JJ_ERR_NO_DEVICE;  // sm_100a code only
     }
     c->sm_count = prop.multiProcessorCount;
+    if (prop.persistingL2CacheMaxSize > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize) == cudaSuccess) {
+        c->l2_persist_max = prop.persistingL2CacheMaxSize;
+        c->l2_window_max = prop.accessPolicyMaxWindowSize;
+    }
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < kStages && ok; k++) ok = cudaStreamCreateWithFlags(&c->st[k].stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
@@ -718,7 +752,8 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
         constexpr int T = 256;
         size_t smem = 64 * 8 * 24 * 4;
         auto kern = k_scalar_mul_fixed<T>;
-        CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // static mbarrier + 48 KB dynamic table exceed the 48 KB default: opt in explicitly
+        CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
         char* dst = dout[0];
         char** tmp = S ? &S->buf[2] : &c->tmp;
         size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;

@@ -356,24 +356,61 @@ __global__ void __launch_bounds__(64) k_fixed_table_build(const char* __restrict
     }
 }
 
+// The shared 48 KB AffineNiels window table is staged into shared memory by ONE bulk asynchronous
+// copy (TMA engine, `cp.async.bulk.shared::cluster.global` -> SASS UBLKCP) that signals an
+// mbarrier with its byte count; the threads of the block wait on the barrier's phase and read
+// their first scalars while the copy is in flight.
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst), bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar), done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+constexpr uint32_t kFixedTableBytes = 64 * 8 * 24 * 4;
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
     k_scalar_mul_fixed(const uint32_t* __restrict__ table, const char* __restrict__ scalars, char* __restrict__ out,
                        size_t n, bool scalar_mont) {
-    extern __shared__ uint4 smem_raw[];
+    extern __shared__ __align__(128) uint4 smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
     uint32_t* stab = (uint32_t*)smem_raw;
-    for (int w = threadIdx.x; w < 64 * 8 * 24 / 4; w += THREADS) smem_raw[w] = ((const uint4*)table)[w];
+    if (threadIdx.x == 0) {
+        uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) tma_bulk_g2s(stab, table, kFixedTableBytes, &mbar);
     fixed_table_view view{stab};
     const size_t stride = (size_t)gridDim.x * THREADS;
+    bool staged = false;
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
         fe k;
         ext_point acc;
-        ld_fe(k, scalars + i * 32);
+        ld_fe(k, scalars + i * 32);  // overlaps the table copy on the first iteration
         if (scalar_mont) fe_to_canonical<FrP>(k, k);
+        if (!staged) {
+            mbar_wait(&mbar, 0);
+            staged = true;
+        }
         scalar_mul_fixed_core(acc, k.w, view);
         st_ext(out, i, acc);
     }
+    if (!staged) mbar_wait(&mbar, 0);  // never leave the block while the bulk copy is in flight
 }
 
 // ---- normalisation / encoding -------------------------------------------------------------------
