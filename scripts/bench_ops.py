@@ -1,0 +1,78 @@
+"""Throughput of every kernel family on device-resident batches (secondary to bench.py).
+Writes gpurun_out/bench_ops.json: ms per launch, units/s, algorithmic GB/s."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import jubjub_b200 as jj  # noqa: E402
+from scripts.run_smul import SEED0, generator  # noqa: E402
+
+
+def timed(eng, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    eng.sync()
+    best = 1e30
+    for _ in range(reps):
+        eng.timer_start()
+        fn()
+        best = min(best, eng.timer_stop())
+    return best
+
+
+def main():
+    eng = jj.Engine(0)
+    n = 1 << int(os.environ.get("OPS_LOGN", "20"))
+    res = {"n": n}
+    A = jj.JJ_ASYNC
+
+    def rec(name, ms, bytes_per_unit):
+        res[name] = {"ms": ms, "units_per_s": n / ms * 1e3, "algorithmic_GBps": n * bytes_per_unit / ms / 1e6}
+        print(f"{name:28s} {ms:9.3f} ms  {n / ms * 1e3:.3e}/s  {n * bytes_per_unit / ms / 1e6:8.1f} GB/s", flush=True)
+
+    for field in ("fq", "fr"):
+        a = eng.fe_stream(field, SEED0, n, device=True)
+        b = eng.fe_stream(field, SEED0 + 1, n, device=True)
+        o = eng.empty((n, 4))
+        rec(f"{field}_mul", timed(eng, lambda: eng.fe_mul(field, a, b, out=o, flags=A)), 96)
+        rec(f"{field}_square", timed(eng, lambda: eng.fe_square(field, a, out=o, flags=A)), 64)
+        rec(f"{field}_add", timed(eng, lambda: eng.fe_add(field, a, b, out=o, flags=A)), 96)
+        rec(f"{field}_sub", timed(eng, lambda: eng.fe_sub(field, a, b, out=o, flags=A)), 96)
+        rec(f"{field}_neg", timed(eng, lambda: eng.fe_neg(field, a, out=o, flags=A)), 64)
+        ok = eng.empty((n, 1), np.uint8)
+        lib, ctx = eng.lib, eng.ctx
+        rec(f"{field}_invert", timed(eng, lambda: eng._check(getattr(lib, f"jj_{field}_invert")(
+            ctx, a.ptr, o.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS | A)), reps=3), 64)
+        for x in (a, b, o, ok):
+            x.free()
+    t = eng.fe_to_bytes("fr", eng.fe_stream("fr", SEED0 + 3, n, device=True))
+    k = eng.fe_to_bytes("fr", eng.fe_stream("fr", SEED0 + 2, n, device=True))
+    gen = generator(eng)
+    p = eng.empty((n, 20))
+    rec("scalar_mul_fixed", timed(eng, lambda: eng.scalar_mul_fixed(gen, t, out=p), reps=3), 192)
+    q = eng.point_double(p)
+    o = eng.empty((n, 20))
+    rec("point_double", timed(eng, lambda: eng._check(eng.lib.jj_point_double(eng.ctx, p.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 320)
+    rec("point_add (ext+ext)", timed(eng, lambda: eng._check(eng.lib.jj_point_add(eng.ctx, p.ptr, q.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 480)
+    nq = eng.point_to_niels(q)
+    rec("point_add_niels", timed(eng, lambda: eng._check(eng.lib.jj_point_add_niels(eng.ctx, p.ptr, nq.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 448)
+    rec("scalar_mul (variable base)", timed(eng, lambda: eng.scalar_mul(p, k, out=o, flags=A), reps=3), 352)
+    aff = eng.empty((n, 8))
+    rec("batch_normalize", timed(eng, lambda: eng.batch_normalize(o, out=aff)), 224)
+    enc = eng.empty((n, 32), np.uint8)
+    rec("affine_to_bytes", timed(eng, lambda: eng.affine_to_bytes(aff, out=enc)), 96)
+    back, ok = eng.empty((n, 8)), eng.empty((n, 1), np.uint8)
+    rec("batch_from_bytes", timed(eng, lambda: eng._check(eng.lib.jj_batch_from_bytes(
+        eng.ctx, enc.ptr, back.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS)), reps=2, warm=1), 96)
+    flg = eng.empty((n, 1), np.uint8)
+    rec("is_torsion_free", timed(eng, lambda: eng._check(eng.lib.jj_is_torsion_free(
+        eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS)), reps=2, warm=1), 161)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/bench_ops.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
