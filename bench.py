@@ -294,6 +294,10 @@ def main():
     sample = min(n, int(os.environ.get("JJ_CPU_SAMPLE", str(12288 * cores))))
     sp, sk = hp[:sample].copy(), hk[:sample].copy()
     cpu_rate, cpu_t = cpu_baseline(sp, sk, cores)
+    from oracle import binding as ob
+
+    cpu_1t = 2048 / ob.time_scalar_mul(sp[:2048], sk[:2048], 1, reps=1)
+    cpu_fq = 10_000_000 / ob.time_fe_mul(ob.FQ, 10_000_000, reps=3)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -324,7 +328,9 @@ def main():
         "fq_mul": fq,
         "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"first {sample} units of the same batch, {cores} threads, {cpu_t:.1f} s, "
-                                   "reference ladder (C restatement in oracle/)"},
+                                   "reference ladder (C restatement in oracle/)",
+                         "single_thread": {"scalar_muls_per_s": cpu_1t, "fq_muls_per_s": cpu_fq,
+                                           "sample": "2048 scalar-muls; 1e7 dependent Fq muls, best of 3"}},
     }
     print(json.dumps(line))
     if dist is not None:

@@ -373,3 +373,18 @@ def test_full_size_linearity_1m(eng, oracle):
     idx = np.arange(0, n, n // 512)[:512]
     ph, ah = pts.download()[idx], oracle.fe_to_bytes(FR, a.download()[idx])
     assert (eng.batch_normalize(pa).download()[idx] == oracle.batch_normalize(oracle.scalar_mul(ph, ah))).all()
+
+
+def test_full_size_fixed_base_1m(eng, oracle):
+    """BASELINE config 4 size (2^20 units): [k]G through the shared per-window table equals [k]G through the
+    variable-base kernel for every unit (two independent kernels), plus an oracle-checked sample."""
+    n = 1 << 20
+    gen = oracle.generator()
+    k = eng.fe_to_bytes("fr", eng.fe_stream("fr", M.SEED0 + 2, n, device=True))
+    fixed = eng.scalar_mul_fixed(gen, k, output="affine").download()
+    pts = eng.to_device(np.repeat(oracle.affine_to_extended(gen), n, axis=0))
+    var = eng.scalar_mul(pts, k, output="affine").download()
+    assert (fixed == var).all()
+    idx = np.arange(0, n, n // 256)[:256]
+    kh = k.download()[idx]
+    assert (fixed[idx] == oracle.batch_normalize(oracle.scalar_mul_fixed(gen, kh))).all()

@@ -338,3 +338,23 @@ def test_r_times_8g_is_identity(oracle):
     gen = oracle.ext_mul_by_cofactor(_ext(oracle, [K.FULL_GENERATOR_RAW]))
     assert oracle.is_torsion_free(gen)[0] == 1
     assert oracle.is_torsion_free(_ext(oracle, [K.FULL_GENERATOR_RAW]))[0] == 0
+
+
+def test_config1_10k_fq_muls_vs_bigint(oracle):
+    """BASELINE.json configs[0]: 10k Fq Montgomery muls on the CPU path (SplitMix64 streams of SURVEY 8d plus the
+    benches/fq_bench.rs:6-7,25-33 values 1, -1, 4), Montgomery limbs bit-exact against the big-integer model."""
+    n = 10_000
+    a, b = oracle.fe_stream(FQ, M.SEED0, n), oracle.fe_stream(FQ, M.SEED0 + 1, n)
+    am, bm = M.stream_field(M.SEED0, n, M.Q), M.stream_field(M.SEED0 + 1, n, M.Q)
+    c = oracle.fe_batch(FQ, oracle.OP_MUL, a, b)
+    for i in range(n):
+        assert to_int(a[i]) == M.to_mont(am[i], M.Q)
+        assert to_int(c[i]) == M.to_mont(am[i] * bm[i] % M.Q, M.Q), i
+    one = oracle.fe_one(FQ)
+    neg_one = oracle.fe_batch(FQ, oracle.OP_NEG, one)
+    x = one
+    for i in range(8):  # `n *= -1` of the bench alternates between -1 and 1
+        x = oracle.fe_batch(FQ, oracle.OP_MUL, x, neg_one)
+        assert (x == (neg_one if i % 2 == 0 else one)).all()
+    four = oracle.fe_batch(FQ, oracle.OP_DOUBLE, oracle.fe_batch(FQ, oracle.OP_DOUBLE, one))
+    assert to_int(four[0]) == M.to_mont(4, M.Q)
