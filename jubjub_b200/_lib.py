@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjubjub_b200.so")
+# JJ_LIB lets kernel experiments load an alternative build of the SAME library (never a fallback)
+LIB_PATH = os.environ.get("JJ_LIB") or os.path.join(_HERE, "libjubjub_b200.so")
 
 # flags (include/jubjub_b200.h)
 JJ_MONT = 0

@@ -163,6 +163,7 @@ const SmulVariant kVariants[] = {
     {256, 2, 2},               // 18: slot-file, 2 x 8 warps/SM
     {448, 1, TABLE_GMEM},      // 19: 14 warps/SM (<= 146 registers)
     {480, 1, TABLE_GMEM},      // 20: 15 warps/SM (<= 136 registers)
+    {256, 2, TABLE_GMEM},      // 21: 16 warps/SM in two blocks (<= 128 registers)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
@@ -247,6 +248,7 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(14, 320, 1, TABLE_GMEM);
         V(19, 448, 1, TABLE_GMEM);
         V(20, 480, 1, TABLE_GMEM);
+        V(21, 256, 2, TABLE_GMEM);
         case 15: return launch_smul_slots<512, 1>(c, s, a, tbl, tbl_cap);
         case 16: return launch_smul_slots<384, 1>(c, s, a, tbl, tbl_cap);
         case 17: return launch_smul_slots<544, 1>(c, s, a, tbl, tbl_cap);

@@ -125,11 +125,14 @@ JJ_DEVICE void into_extended(ext_point& r, const fe& cu, const fe& cv, const fe&
     r.z = z;
 }
 
-#if defined(JJ_DOUBLE_INLINE)
+#if defined(JJ_DOUBLE_INLINE) || defined(JJ_DOUBLE_INLINE_SQR)
 #define JJ_DBL_SQR(r, a) mont_sqr<FqP>(r, a)
-#define JJ_DBL_MUL(r, a, b) mont_mul<FqP>(r, a, b)
 #else
 #define JJ_DBL_SQR(r, a) fq_sqr(r, a)
+#endif
+#if defined(JJ_DOUBLE_INLINE) || defined(JJ_DOUBLE_INLINE_MUL)
+#define JJ_DBL_MUL(r, a, b) mont_mul<FqP>(r, a, b)
+#else
 #define JJ_DBL_MUL(r, a, b) fq_mul(r, a, b)
 #endif
 JJ_DEVICE void point_double(ext_point& r, const ext_point& p) {
