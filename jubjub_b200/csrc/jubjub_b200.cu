@@ -512,7 +512,7 @@ int32_t jj_sync(jj_ctx* c) {
 const char* jj_last_error(const jj_ctx* c) { return c ? c->err : "null context"; }
 uint64_t jj_launch_count(const jj_ctx* c) { return c ? c->launches : 0; }
 int32_t jj_set_scalar_mul_variant(jj_ctx* c, int32_t v) {
-    if (!c || v < 0 || v >= kNumVariants) return JJ_ERR_INVALID_ARG;
+    if (!c || v < 0 || (v >= kNumVariants && v != 100)) return JJ_ERR_INVALID_ARG;  // 100: fixed-base kernel with shared Fq bodies
     c->smul_variant = v;
     return JJ_OK;
 }
@@ -753,7 +753,7 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
         constexpr int T = 256;
         size_t smem = 64 * 8 * 24 * 4;
-        auto kern = k_scalar_mul_fixed<T>;
+        auto kern = c->smul_variant == 100 ? k_scalar_mul_fixed<T, false> : k_scalar_mul_fixed<T, true>;
         // static mbarrier + 48 KB dynamic table exceed the 48 KB default: opt in explicitly
         CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
         char* dst = dout[0];

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) k_point_op(const char* __restrict__ p, co
             aff_niels nn;
             ld_fe(a.u, p + i * 64);
             ld_fe(a.v, p + i * 64 + 32);
-            affine_to_niels(nn, a);
+            affine_to_niels_t<true>(nn, a);
             st_fe(out + i * 96, nn.vpu);
             st_fe(out + i * 96 + 32, nn.vmu);
             st_fe(out + i * 96 + 64, nn.t2d);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128) k_point_op(const char* __restrict__ p, co
         ld_ext(P, p, i);
         if (OP == PT_TO_NIELS) {
             ext_niels nn;
-            point_to_niels(nn, P);
+            point_to_niels_t<true>(nn, P);
             st_fe(out + i * 128, nn.vpu);
             st_fe(out + i * 128 + 32, nn.vmu);
             st_fe(out + i * 128 + 64, nn.z);
@@ -157,24 +157,24 @@ __global__ void __launch_bounds__(128) k_point_op(const char* __restrict__ p, co
             continue;
         }
         if (OP == PT_DBL) {
-            point_double(R, P);
+            point_double_t<true>(R, P);
         } else if (OP == PT_ADD) {
             ext_point Q;
             ld_ext(Q, q, i);
-            point_add(R, P, Q, sub);
+            point_add_t<true>(R, P, Q, sub);
         } else if (OP == PT_ADD_NIELS) {
             ext_niels nn;
             ld_fe(nn.vpu, q + i * 128);
             ld_fe(nn.vmu, q + i * 128 + 32);
             ld_fe(nn.z, q + i * 128 + 64);
             ld_fe(nn.t2d, q + i * 128 + 96);
-            point_add_niels(R, P, nn, sub);
+            point_add_niels_t<true>(R, P, nn, sub);
         } else {
             aff_niels nn;
             ld_fe(nn.vpu, q + i * 96);
             ld_fe(nn.vmu, q + i * 96 + 32);
             ld_fe(nn.t2d, q + i * 96 + 64);
-            point_add_aff_niels(R, P, nn, sub);
+            point_add_aff_niels_t<true>(R, P, nn, sub);
         }
         st_ext(out, i, R);
     }
@@ -381,7 +381,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
 }
 constexpr uint32_t kFixedTableBytes = 64 * 8 * 24 * 4;
 
-template <int THREADS>
+template <int THREADS, bool INL>
 __global__ void __launch_bounds__(THREADS)
     k_scalar_mul_fixed(const uint32_t* __restrict__ table, const char* __restrict__ scalars, char* __restrict__ out,
                        size_t n, bool scalar_mont) {
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(THREADS)
             mbar_wait(&mbar, 0);
             staged = true;
         }
-        scalar_mul_fixed_core(acc, k.w, view);
+        scalar_mul_fixed_core<INL>(acc, k.w, view);
         st_ext(out, i, acc);
     }
     if (!staged) mbar_wait(&mbar, 0);  // never leave the block while the bulk copy is in flight

@@ -112,65 +112,72 @@ JJ_DEVICE void point_neg(ext_point& r, const ext_point& p) {  // src/lib.rs:196-
     r.t2 = p.t2;
 }
 
-// completed point (u, v, z, t) -> extended (u*t, v*z, z*t, u, v)
-JJ_DEVICE void into_extended(ext_point& r, const fe& cu, const fe& cv, const fe& cz, const fe& ct) {
+// Every formula exists in two instantiations: INL = true inlines the Fq product / square bodies
+// (best for kernels that use a formula once: the elementwise point kernels, the fixed-base loop, the
+// doubling of the variable-base loop), INL = false calls the shared noinline bodies (small code).
+template <bool INL>
+JJ_DEVICE void fqm(fe& r, const fe& a, const fe& b) {
+    if (INL) mont_mul<FqP>(r, a, b);
+    else fq_mul(r, a, b);
+}
+template <bool INL>
+JJ_DEVICE void fqs(fe& r, const fe& a) {
+    if (INL) mont_sqr<FqP>(r, a);
+    else fq_sqr(r, a);
+}
+#if defined(JJ_DOUBLE_INLINE)
+constexpr bool kInlineDouble = true;
+#else
+constexpr bool kInlineDouble = false;
+#endif
+
+// completed point (u, v, z, t) -> extended (u*t, v*z, z*t, u, v)   (src/lib.rs:1052-1060)
+template <bool INL>
+JJ_DEVICE void into_extended_t(ext_point& r, const fe& cu, const fe& cv, const fe& cz, const fe& ct) {
     fe u, v, z;
-    fq_mul(u, cu, ct);
-    fq_mul(v, cv, cz);
-    fq_mul(z, cz, ct);
+    fqm<INL>(u, cu, ct);
+    fqm<INL>(v, cv, cz);
+    fqm<INL>(z, cz, ct);
     r.t1 = cu;
     r.t2 = cv;
     r.u = u;
     r.v = v;
     r.z = z;
 }
-
-#if defined(JJ_DOUBLE_INLINE) || defined(JJ_DOUBLE_INLINE_SQR)
-#define JJ_DBL_SQR(r, a) mont_sqr<FqP>(r, a)
-#else
-#define JJ_DBL_SQR(r, a) fq_sqr(r, a)
-#endif
-#if defined(JJ_DOUBLE_INLINE) || defined(JJ_DOUBLE_INLINE_MUL)
-#define JJ_DBL_MUL(r, a, b) mont_mul<FqP>(r, a, b)
-#else
-#define JJ_DBL_MUL(r, a, b) fq_mul(r, a, b)
-#endif
-JJ_DEVICE void point_double(ext_point& r, const ext_point& p) {
+template <bool INL>
+JJ_DEVICE void point_double_t(ext_point& r, const ext_point& p) {
     fe uu, vv, zz2, uv2, vpu, vmu, cu, ct;
-    JJ_DBL_SQR(uu, p.u);
-    JJ_DBL_SQR(vv, p.v);
-    JJ_DBL_SQR(zz2, p.z);
+    fqs<INL>(uu, p.u);
+    fqs<INL>(vv, p.v);
+    fqs<INL>(zz2, p.z);
     fe_dbl<FqP>(zz2, zz2);
     fe_add<FqP>(uv2, p.u, p.v);
-    JJ_DBL_SQR(uv2, uv2);
+    fqs<INL>(uv2, uv2);
     fe_add<FqP>(vpu, vv, uu);
     fe_sub<FqP>(vmu, vv, uu);
     fe_sub<FqP>(cu, uv2, vpu);
     fe_sub<FqP>(ct, zz2, vmu);
-    fe u, v, z;  // into_extended (src/lib.rs:1052-1060)
-    JJ_DBL_MUL(u, cu, ct);
-    JJ_DBL_MUL(v, vpu, vmu);
-    JJ_DBL_MUL(z, vmu, ct);
-    r.t1 = cu;
-    r.t2 = vpu;
-    r.u = u;
-    r.v = v;
-    r.z = z;
+    into_extended_t<INL>(r, cu, vpu, vmu, ct);
 }
-
-// p + n (sub = false) or p - n (sub = true) for an extended-Niels operand.
-JJ_DEVICE void point_add_niels(ext_point& r, const ext_point& p, const ext_niels& n, bool sub) {
+// p + n (sub = false) or p - n (sub = true); Z2 = nullptr means an affine-Niels operand (d = 2z).
+template <bool INL>
+JJ_DEVICE void point_add_core_t(ext_point& r, const ext_point& p, const fe& n_vpu, const fe& n_vmu, const fe* n_z,
+                                const fe& n_t2d, bool sub) {
     fe a, b, c, d, t, n1, n2;
-    fe_select(n1, n.vmu, n.vpu, sub);  // multiplies (v - u)
-    fe_select(n2, n.vpu, n.vmu, sub);  // multiplies (v + u)
+    fe_select(n1, n_vmu, n_vpu, sub);  // multiplies (v - u)
+    fe_select(n2, n_vpu, n_vmu, sub);  // multiplies (v + u)
     fe_sub<FqP>(t, p.v, p.u);
-    fq_mul(a, t, n1);
+    fqm<INL>(a, t, n1);
     fe_add<FqP>(t, p.v, p.u);
-    fq_mul(b, t, n2);
-    fq_mul(c, p.t1, p.t2);
-    fq_mul(c, c, n.t2d);
-    fq_mul(d, p.z, n.z);
-    fe_dbl<FqP>(d, d);
+    fqm<INL>(b, t, n2);
+    fqm<INL>(c, p.t1, p.t2);
+    fqm<INL>(c, c, n_t2d);
+    if (n_z) {
+        fqm<INL>(d, p.z, *n_z);
+        fe_dbl<FqP>(d, d);
+    } else {
+        fe_dbl<FqP>(d, p.z);
+    }
     fe cu, cv, dpc, dmc, cz, ct;
     fe_sub<FqP>(cu, b, a);
     fe_add<FqP>(cv, b, a);
@@ -178,53 +185,50 @@ JJ_DEVICE void point_add_niels(ext_point& r, const ext_point& p, const ext_niels
     fe_sub<FqP>(dmc, d, c);
     fe_select(cz, dpc, dmc, sub);
     fe_select(ct, dmc, dpc, sub);
-    into_extended(r, cu, cv, cz, ct);
+    into_extended_t<INL>(r, cu, cv, cz, ct);
 }
-// p +/- n for an affine-Niels operand (n.z == 1, so d = 2z).
-JJ_DEVICE void point_add_aff_niels(ext_point& r, const ext_point& p, const aff_niels& n, bool sub) {
-    fe a, b, c, d, t, n1, n2;
-    fe_select(n1, n.vmu, n.vpu, sub);
-    fe_select(n2, n.vpu, n.vmu, sub);
-    fe_sub<FqP>(t, p.v, p.u);
-    fq_mul(a, t, n1);
-    fe_add<FqP>(t, p.v, p.u);
-    fq_mul(b, t, n2);
-    fq_mul(c, p.t1, p.t2);
-    fq_mul(c, c, n.t2d);
-    fe_dbl<FqP>(d, p.z);
-    fe cu, cv, dpc, dmc, cz, ct;
-    fe_sub<FqP>(cu, b, a);
-    fe_add<FqP>(cv, b, a);
-    fe_add<FqP>(dpc, d, c);
-    fe_sub<FqP>(dmc, d, c);
-    fe_select(cz, dpc, dmc, sub);
-    fe_select(ct, dmc, dpc, sub);
-    into_extended(r, cu, cv, cz, ct);
+template <bool INL>
+JJ_DEVICE void point_add_niels_t(ext_point& r, const ext_point& p, const ext_niels& n, bool sub) {
+    point_add_core_t<INL>(r, p, n.vpu, n.vmu, &n.z, n.t2d, sub);
 }
-
-JJ_DEVICE void point_to_niels(ext_niels& n, const ext_point& p) {
+template <bool INL>
+JJ_DEVICE void point_add_aff_niels_t(ext_point& r, const ext_point& p, const aff_niels& n, bool sub) {
+    point_add_core_t<INL>(r, p, n.vpu, n.vmu, nullptr, n.t2d, sub);
+}
+template <bool INL>
+JJ_DEVICE void point_to_niels_t(ext_niels& n, const ext_point& p) {
     fe d2, t;
     JJ_LOAD_CONST(d2, Curve::D2);
     fe_add<FqP>(n.vpu, p.v, p.u);
     fe_sub<FqP>(n.vmu, p.v, p.u);
     n.z = p.z;
-    fq_mul(t, p.t1, p.t2);
-    fq_mul(n.t2d, t, d2);
+    fqm<INL>(t, p.t1, p.t2);
+    fqm<INL>(n.t2d, t, d2);
 }
-JJ_DEVICE void affine_to_niels(aff_niels& n, const aff_point& p) {
+template <bool INL>
+JJ_DEVICE void affine_to_niels_t(aff_niels& n, const aff_point& p) {
     fe d2, t;
     JJ_LOAD_CONST(d2, Curve::D2);
     fe_add<FqP>(n.vpu, p.v, p.u);
     fe_sub<FqP>(n.vmu, p.v, p.u);
-    fq_mul(t, p.u, p.v);
-    fq_mul(n.t2d, t, d2);
+    fqm<INL>(t, p.u, p.v);
+    fqm<INL>(n.t2d, t, d2);
 }
 // p + q with both extended: q.to_niels() then the 8M add (src/lib.rs:992-999).
-JJ_DEVICE void point_add(ext_point& r, const ext_point& p, const ext_point& q, bool sub) {
+template <bool INL>
+JJ_DEVICE void point_add_t(ext_point& r, const ext_point& p, const ext_point& q, bool sub) {
     ext_niels n;
-    point_to_niels(n, q);
-    point_add_niels(r, p, n, sub);
+    point_to_niels_t<INL>(n, q);
+    point_add_niels_t<INL>(r, p, n, sub);
 }
+// default instantiations used by the scalar-mul cores
+JJ_DEVICE void point_double(ext_point& r, const ext_point& p) { point_double_t<kInlineDouble>(r, p); }
+JJ_DEVICE void point_add_niels(ext_point& r, const ext_point& p, const ext_niels& n, bool sub) { point_add_niels_t<false>(r, p, n, sub); }
+JJ_DEVICE void point_add_aff_niels(ext_point& r, const ext_point& p, const aff_niels& n, bool sub) { point_add_aff_niels_t<false>(r, p, n, sub); }
+JJ_DEVICE void point_to_niels(ext_niels& n, const ext_point& p) { point_to_niels_t<false>(n, p); }
+JJ_DEVICE void affine_to_niels(aff_niels& n, const aff_point& p) { affine_to_niels_t<false>(n, p); }
+JJ_DEVICE void point_add(ext_point& r, const ext_point& p, const ext_point& q, bool sub) { point_add_t<false>(r, p, q, sub); }
+
 // AffinePoint::from_bytes_inner (src/lib.rs:492-534) for one encoding held as 8 LE words.
 // Returns false (and leaves the zero point) for non-canonical v, off-curve v, or -- with zip216 --
 // the non-canonical encodings of (0, +-1) whose sign bit is set (ZIP 216, src/lib.rs:527-531).

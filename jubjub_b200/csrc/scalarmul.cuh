@@ -108,6 +108,7 @@ struct fixed_table_view {
         }
     }
 };
+template <bool INL>
 JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const fixed_table_view& tbl) {
     uint32_t t[8];
     add_cc(t[0], k[0], 0x88888888u);
@@ -124,7 +125,7 @@ JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const 
         if (d != 0) {
             aff_niels n;
             tbl.load(i, (d < 0 ? -d : d) - 1, n);
-            point_add_aff_niels(acc, acc, n, d < 0);
+            point_add_aff_niels_t<INL>(acc, acc, n, d < 0);
         }
     }
 }

@@ -94,7 +94,7 @@ extern "C" void emul_scalar_mul_fixed(const uint32_t* table, const void* k_, voi
     fixed_table_view v{table};
     for (size_t i = 0; i < n; i++) {
         ext_point acc;
-        scalar_mul_fixed_core(acc, ((const uint32_t*)k_) + 8 * i, v);
+        scalar_mul_fixed_core<true>(acc, ((const uint32_t*)k_) + 8 * i, v);
         ((ext_point*)out_)[i] = acc;
     }
 }
