@@ -90,6 +90,7 @@ struct jj_ctx {
     char* fixed_base_dev = nullptr;   // 64 B
     char fixed_base_key[64];
     bool fixed_valid = false;
+    int fixed_w = 0;
     char* const_scalar = nullptr;  // r, for is_torsion_free
     char* flush = nullptr;
     size_t flush_bytes = 0;
@@ -416,24 +417,47 @@ int32_t finish_output(jj_ctx* c, cudaStream_t s, const char* ext, char* out, siz
 }
 size_t out_unit(uint32_t flags) { return (flags & JJ_OUT_BYTES) ? 32 : (flags & JJ_OUT_AFFINE) ? 64 : 160; }
 
+// fixed-base window width: 7 (216 KB table, the default) or 4 (47 KB table, variant 100)
+int fixed_w(const jj_ctx* c) { return c->smul_variant == 100 ? 4 : 7; }
+
 int32_t build_fixed_table(jj_ctx* c, const void* base_affine, uint32_t flags) {
     char key[64];
     if (flags & JJ_DEVICE_PTRS)
         CU(c, cudaMemcpy(key, base_affine, 64, cudaMemcpyDeviceToHost));
     else
         memcpy(key, base_affine, 64);
-    if (c->fixed_valid && memcmp(key, c->fixed_base_key, 64) == 0) return JJ_OK;
-    if (!c->fixed_table) CU(c, cudaMalloc((void**)&c->fixed_table, 64 * 8 * 24 * 4));
+    const int w = fixed_w(c);
+    if (c->fixed_valid && c->fixed_w == w && memcmp(key, c->fixed_base_key, 64) == 0) return JJ_OK;
+    if (!c->fixed_table) CU(c, cudaMalloc((void**)&c->fixed_table, FixedGeom<7>::BYTES));
     if (!c->fixed_base_dev) CU(c, cudaMalloc((void**)&c->fixed_base_dev, 64));
     CU(c, cudaMemcpy(c->fixed_base_dev, key, 64, cudaMemcpyHostToDevice));
-    int32_t rc = ensure(c, &c->tbl, &c->tbl_cap, (size_t)16 * 32768);
+    const int entries = w == 4 ? FixedGeom<4>::ENTRIES : FixedGeom<7>::ENTRIES;
+    const int blocks = (entries + 63) / 64;
+    int32_t rc = ensure(c, &c->tbl, &c->tbl_cap, (size_t)(blocks * 2) * 32768);
     if (rc) return rc;
-    k_fixed_table_build<<<8, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
+    if (w == 4)
+        k_fixed_table_build<4><<<blocks, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
+    else
+        k_fixed_table_build<7><<<blocks, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
     c->launches++;
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));
     memcpy(c->fixed_base_key, key, 64);
     c->fixed_valid = true;
+    c->fixed_w = w;
+    return JJ_OK;
+}
+
+template <int T, int W, bool INL>
+int32_t launch_fixed(jj_ctx* c, cudaStream_t s, const char* scalars, char* dst, size_t cnt, bool smont) {
+    auto kern = k_scalar_mul_fixed<T, W, INL>;
+    size_t smem = FixedGeom<W>::BYTES;
+    // static mbarrier + dynamic table: opt in explicitly
+    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+    const int per_sm = smem > 100000 ? 1 : 2;
+    kern<<<grid_for(c, cnt, T, per_sm), T, smem, s>>>(c->fixed_table, scalars, dst, cnt, smont);
+    c->launches++;
+    CU(c, cudaGetLastError());
     return JJ_OK;
 }
 
@@ -751,11 +775,6 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
     Out outs[2] = {{out, out_unit(flags)}, {nullptr, 0}};
     bool smont = flags & JJ_SCALAR_MONT, conv = flags & (JJ_OUT_AFFINE | JJ_OUT_BYTES);
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
-        constexpr int T = 256;
-        size_t smem = 64 * 8 * 24 * 4;
-        auto kern = c->smul_variant == 100 ? k_scalar_mul_fixed<T, false> : k_scalar_mul_fixed<T, true>;
-        // static mbarrier + 48 KB dynamic table exceed the 48 KB default: opt in explicitly
-        CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
         char* dst = dout[0];
         char** tmp = S ? &S->buf[2] : &c->tmp;
         size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;
@@ -764,9 +783,9 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
             if (rc) return rc;
             dst = *tmp;
         }
-        kern<<<grid_for(c, cnt, T, 2), T, smem, s>>>(c->fixed_table, din[0], dst, cnt, smont);
-        c->launches++;
-        CU(c, cudaGetLastError());
+        int32_t rc = fixed_w(c) == 4 ? launch_fixed<256, 4, false>(c, s, din[0], dst, cnt, smont)
+                                     : launch_fixed<512, 7, true>(c, s, din[0], dst, cnt, smont);
+        if (rc) return rc;
         if (conv) return finish_output(c, s, dst, dout[0], cnt, flags, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap);
         return JJ_OK;
     });

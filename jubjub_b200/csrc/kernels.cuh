@@ -317,13 +317,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul_slots(const 
 }
 
 // ---- fixed-base scalar multiplication -----------------------------------------------------------
-// Builds entry (i, j) = AffineNiels((j+1) * 16^i * B): thread (i, j) runs the variable-base
-// core on a small scalar, shifts by one window with four doublings, normalises with one
-// Fermat inversion.  512 threads, once per base.
+// Builds entry e of the fixed-base table (scalarmul.cuh): thread e runs the variable-base core on
+// the small scalar (j+1) << (W*i) -- the top-carry entry on 1 << (W*(NW-1)) followed by W doublings --
+// and normalises with one Fermat inversion.  Once per base.
+template <int W>
 __global__ void __launch_bounds__(64) k_fixed_table_build(const char* __restrict__ base_affine,
                                                           uint32_t* __restrict__ table, char* __restrict__ scratch) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;  // 0..511
-    int i = e >> 3, j = e & 7;
+    using G = FixedGeom<W>;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= G::ENTRIES) return;
+    const bool top = e == G::NW * G::PER;
+    int i = top ? G::NW - 1 : e / G::PER, j = top ? 0 : e % G::PER;
     aff_point B;
     ld_fe(B.u, base_affine);
     ld_fe(B.v, base_affine + 32);
@@ -331,15 +335,20 @@ __global__ void __launch_bounds__(64) k_fixed_table_build(const char* __restrict
     point_from_affine(P, B);
     fe k;
     fe_set_zero(k);
-    int sh = i > 0 ? i - 1 : 0;
+    {   // k = (j + 1) << (W * i); spans at most two words
+        const int bit = W * i;
+        uint64_t v = (uint64_t)(j + 1) << (bit & 31);
 #pragma unroll
-    for (int w = 0; w < 8; w++)
-        if (w == (sh >> 3)) k.w[w] = (uint32_t)(j + 1) << (4 * (sh & 7));
+        for (int w = 0; w < 8; w++) {
+            if (w == (bit >> 5)) k.w[w] = (uint32_t)v;
+            if (w == (bit >> 5) + 1) k.w[w] = (uint32_t)(v >> 32);
+        }
+    }
     size_t gwarp = (size_t)e >> 5;
     GmemTable t{scratch + gwarp * 32768 + (e & 31) * 32};
     scalar_mul_core(acc, P, k.w, t);
-    if (i > 0)
-        for (int d = 0; d < 4; d++) point_double(acc, acc);
+    if (top)
+        for (int d = 0; d < W; d++) point_double(acc, acc);
     fe zi;
     fe_invert<FqP>(zi, acc.z);
     aff_point a;
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(64) k_fixed_table_build(const char* __restrict
     mont_mul<FqP>(a.u, acc.u, zi);
     mont_mul<FqP>(a.v, acc.v, zi);
     affine_to_niels(nn, a);
-    uint32_t* dst = table + e * 24;
+    uint32_t* dst = table + (size_t)e * 24;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         dst[w] = nn.vpu.w[w];
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(64) k_fixed_table_build(const char* __restrict
     }
 }
 
-// The shared 48 KB AffineNiels window table is staged into shared memory by ONE bulk asynchronous
+// The shared AffineNiels window table (216 KB for W = 7) is staged into shared memory by ONE bulk asynchronous
 // copy (TMA engine, `cp.async.bulk.shared::cluster.global` -> SASS UBLKCP) that signals an
 // mbarrier with its byte count; the threads of the block wait on the barrier's phase and read
 // their first scalars while the copy is in flight.
@@ -379,9 +388,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
             : "memory");
     }
 }
-constexpr uint32_t kFixedTableBytes = 64 * 8 * 24 * 4;
-
-template <int THREADS, bool INL>
+template <int THREADS, int W, bool INL>
 __global__ void __launch_bounds__(THREADS)
     k_scalar_mul_fixed(const uint32_t* __restrict__ table, const char* __restrict__ scalars, char* __restrict__ out,
                        size_t n, bool scalar_mont) {
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(THREADS)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) tma_bulk_g2s(stab, table, kFixedTableBytes, &mbar);
+    if (threadIdx.x == 0) tma_bulk_g2s(stab, table, FixedGeom<W>::BYTES, &mbar);
     fixed_table_view view{stab};
     const size_t stride = (size_t)gridDim.x * THREADS;
     bool staged = false;
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(THREADS)
             mbar_wait(&mbar, 0);
             staged = true;
         }
-        scalar_mul_fixed_core<INL>(acc, k.w, view);
+        scalar_mul_fixed_core<W, INL>(acc, k.w, view);
         st_ext(out, i, acc);
     }
     if (!staged) mbar_wait(&mbar, 0);  // never leave the block while the bulk copy is in flight

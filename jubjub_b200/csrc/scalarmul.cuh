@@ -93,13 +93,22 @@ JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_
 }
 
 // ---- fixed base -------------------------------------------------------------------------
-// Shared per-window table: entry (i, j) = affine-Niels of (j+1) * 16^i * B, i = 0..63,
-// j = 0..7  (64 * 8 * 96 B = 48 KB).  [k]B = sum_i d_i * 16^i * B needs no doublings:
-// <= 64 mixed additions of 7M each (src/lib.rs:944-988).
+// Shared per-window table for one base B: entry (i, j) = affine-Niels of (j+1) * 2^(W*i) * B for
+// window i < NW = ceil(252 / W) and j < 2^(W-1), plus one entry 2^(W*NW) * B for the recoding's top
+// carry.  [k]B = sum_i d_i * 2^(W*i) * B with signed digits d_i in [-2^(W-1), 2^(W-1) - 1] needs no
+// doublings: <= NW + 1 mixed additions of 7M each (src/lib.rs:944-988).  W = 7: 36 windows x 64
+// entries x 96 B = 216 KB, the whole shared memory of an SM; W = 4: 63 windows, 47 KB.
+template <int W>
+struct FixedGeom {
+    static constexpr int NW = (252 + W - 1) / W;
+    static constexpr int PER = 1 << (W - 1);
+    static constexpr int ENTRIES = NW * PER + 1;
+    static constexpr uint32_t BYTES = (uint32_t)ENTRIES * 96u;
+};
 struct fixed_table_view {
-    const uint32_t* base;  // [i][j][24 words]
-    JJ_DEVICE_SPEC void load(int i, int j, aff_niels& n) const {
-        const uint32_t* p = base + (i * 8 + j) * 24;
+    const uint32_t* base;  // [entry][24 words]
+    JJ_DEVICE_SPEC void load(int entry, aff_niels& n) const {
+        const uint32_t* p = base + entry * 24;
 #pragma unroll
         for (int w = 0; w < 8; w++) {
             n.vpu.w[w] = p[w];
@@ -108,23 +117,37 @@ struct fixed_table_view {
         }
     }
 };
-template <bool INL>
-JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const fixed_table_view& tbl) {
-    uint32_t t[8];
-    add_cc(t[0], k[0], 0x88888888u);
+// t = (k mod 2^252) + sum_{i < NW} 2^(W-1) * 2^(W*i): window i of t, minus 2^(W-1), is digit d_i.
+template <int W>
+JJ_DEVICE void recode_fixed(uint32_t t[8], const uint32_t k[8]) {
+    uint32_t c[8];
 #pragma unroll
-    for (int i = 1; i < 7; i++) addc_cc(t[i], k[i], 0x88888888u);
-    addc(t[7], k[7] & 0x0fffffffu, 0x08888888u);
+    for (int w = 0; w < 8; w++) c[w] = 0;
+#pragma unroll
+    for (int i = 0; i < FixedGeom<W>::NW; i++) {
+        const int bit = W * i + W - 1;
+        c[bit >> 5] |= 1u << (bit & 31);
+    }
+    add_cc(t[0], k[0], c[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(t[i], k[i], c[i]);
+    addc(t[7], k[7] & 0x0fffffffu, c[7]);
+}
+template <int W, bool INL>
+JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const fixed_table_view& tbl) {
+    constexpr int NW = FixedGeom<W>::NW, PER = FixedGeom<W>::PER;
+    uint32_t t[8];
+    recode_fixed<W>(t, k);
     point_set_identity(acc);
 #pragma unroll 1
-    for (int i = 0; i < 64; i++) {
-        int d = (int)(t[0] & 15u) - (i < 63 ? 8 : 0);
+    for (int i = 0; i <= NW; i++) {
+        int d = (int)(t[0] & ((1u << W) - 1u)) - (i < NW ? PER : 0);
 #pragma unroll
-        for (int w = 0; w < 7; w++) t[w] = (t[w] >> 4) | (t[w + 1] << 28);
-        t[7] >>= 4;
+        for (int w = 0; w < 7; w++) t[w] = (t[w] >> W) | (t[w + 1] << (32 - W));
+        t[7] >>= W;
         if (d != 0) {
             aff_niels n;
-            tbl.load(i, (d < 0 ? -d : d) - 1, n);
+            tbl.load(i * PER + (d < 0 ? -d : d) - 1, n);
             point_add_aff_niels_t<INL>(acc, acc, n, d < 0);
         }
     }

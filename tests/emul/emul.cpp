@@ -65,40 +65,50 @@ extern "C" void emul_scalar_mul(const void* p_, const void* k_, void* out_, size
         ((ext_point*)out_)[i] = acc;
     }
 }
-// table[(i*8+j)*24 ..] = affine-Niels((j+1) * 16^i * base)
-extern "C" void emul_fixed_table(const void* base_affine, uint32_t* table) {
+// fixed-base table for window width W (4 or 7), same construction as k_fixed_table_build
+template <int W>
+static void fixed_table(const void* base_affine, uint32_t* table, int first, int count) {
+    using G = FixedGeom<W>;
     ext_point B;
     point_from_affine(B, *(const aff_point*)base_affine);
-    for (int i = 0; i < 64; i++)
-        for (int j = 0; j < 8; j++) {
-            // (j+1) * 16^i = 16 * ((j+1) * 16^(i-1)): keeps the scalar below 2^252
-            uint32_t k[8] = {0};
-            int sh = i > 0 ? i - 1 : 0;
-            k[sh / 8] = (uint32_t)(j + 1) << (4 * (sh % 8));
-            LocalTable tbl;
-            ext_point acc;
-            scalar_mul_core(acc, B, k, tbl);
-            if (i > 0)
-                for (int d = 0; d < 4; d++) point_double(acc, acc);
-            fe zi;
-            fe_invert<FqP>(zi, acc.z);
-            aff_point a;
-            mont_mul<FqP>(a.u, acc.u, zi);
-            mont_mul<FqP>(a.v, acc.v, zi);
-            aff_niels nn;
-            affine_to_niels(nn, a);
-            std::memcpy(table + (i * 8 + j) * 24, &nn, 96);
-        }
+    for (int e = first; e < G::ENTRIES && e < first + count; e++) {
+        const bool top = e == G::NW * G::PER;
+        int i = top ? G::NW - 1 : e / G::PER, j = top ? 0 : e % G::PER;
+        uint32_t k[8] = {0};
+        const int bit = W * i;
+        uint64_t v = (uint64_t)(j + 1) << (bit & 31);
+        k[bit >> 5] = (uint32_t)v;
+        if ((bit >> 5) + 1 < 8) k[(bit >> 5) + 1] = (uint32_t)(v >> 32);
+        LocalTable tbl;
+        ext_point acc;
+        scalar_mul_core(acc, B, k, tbl);
+        if (top)
+            for (int d = 0; d < W; d++) point_double(acc, acc);
+        fe zi;
+        fe_invert<FqP>(zi, acc.z);
+        aff_point a;
+        mont_mul<FqP>(a.u, acc.u, zi);
+        mont_mul<FqP>(a.v, acc.v, zi);
+        aff_niels nn;
+        affine_to_niels(nn, a);
+        std::memcpy(table + (size_t)e * 24, &nn, 96);
+    }
 }
-extern "C" void emul_scalar_mul_fixed(const uint32_t* table, const void* k_, void* out_, size_t n) {
+extern "C" int emul_fixed_table_words(int w) { return (w == 4 ? FixedGeom<4>::ENTRIES : FixedGeom<7>::ENTRIES) * 24; }
+// builds entries [first, first + count) of the table in place
+extern "C" void emul_fixed_table(const void* base_affine, uint32_t* table, int w, int first, int count) {
+    if (w == 4) fixed_table<4>(base_affine, table, first, count);
+    else fixed_table<7>(base_affine, table, first, count);
+}
+extern "C" void emul_scalar_mul_fixed(const uint32_t* table, const void* k_, void* out_, size_t n, int w) {
     fixed_table_view v{table};
     for (size_t i = 0; i < n; i++) {
         ext_point acc;
-        scalar_mul_fixed_core<true>(acc, ((const uint32_t*)k_) + 8 * i, v);
+        if (w == 4) scalar_mul_fixed_core<4, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
+        else scalar_mul_fixed_core<7, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
         ((ext_point*)out_)[i] = acc;
     }
 }
-
 extern "C" void emul_from_bytes(const void* in32, void* out_affine, uint8_t* ok, int zip216, size_t n) {
     for (size_t i = 0; i < n; i++) {
         aff_point p;

@@ -219,7 +219,16 @@ def test_mul_consistency_and_assoc(eng, oracle):
     assert oracle.ext_eq(lhs, eng.scalar_mul(p, scalar_bytes(3938000)))[0]
 
 
-def test_scalar_mul_fixed(eng, oracle):
+@pytest.mark.parametrize("variant", [0, 100])  # 0: 7-bit windows (216 KB table); 100: 4-bit windows (47 KB)
+def test_scalar_mul_fixed(eng, oracle, variant):
+    eng.set_scalar_mul_variant(variant)
+    try:
+        _check_fixed(eng, oracle)
+    finally:
+        eng.set_scalar_mul_variant(0)
+
+
+def _check_fixed(eng, oracle):
     k = np.concatenate([scalar_bytes(*EDGE_SCALARS), oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 5, 2000))])
     for base in (oracle.generator(), oracle.ext_to_affine(oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator())))):
         want = oracle.batch_normalize(oracle.scalar_mul_fixed(base, k))

@@ -84,13 +84,22 @@ def emul(built):
             return out
 
         @staticmethod
-        def smul_fixed(base, k):
-            tbl = np.zeros(64 * 8 * 24, dtype=np.uint32)
-            lib.emul_fixed_table(base.ctypes.data_as(C.c_void_p), tbl.ctypes.data_as(C.c_void_p))
+        def fixed_entries(base, w, first, count):
+            tbl = np.zeros(lib.emul_fixed_table_words(w), dtype=np.uint32)
+            lib.emul_fixed_table(base.ctypes.data_as(C.c_void_p), tbl.ctypes.data_as(C.c_void_p), w, first, count)
+            return tbl.reshape(-1, 24)[first:first + count]
+
+        @staticmethod
+        def smul_fixed(tbl, k, w):
+            tbl = np.ascontiguousarray(tbl, dtype=np.uint32)
             out = np.empty((len(k), 20), dtype=np.uint64)
             lib.emul_scalar_mul_fixed(tbl.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),
-                                      out.ctypes.data_as(C.c_void_p), C.c_size_t(len(k)))
+                                      out.ctypes.data_as(C.c_void_p), C.c_size_t(len(k)), w)
             return out
+
+        @staticmethod
+        def table_words(w):
+            return lib.emul_fixed_table_words(w)
 
     return E
 
@@ -137,8 +146,24 @@ def test_emulated_points_and_scalar_mul(emul, oracle):
     got = emul.smul(pp, k)
     assert oracle.ext_eq(got, want).all()
     assert (oracle.batch_normalize(got) == oracle.batch_normalize(want)).all()
-    got = emul.smul_fixed(oracle.generator(), k)
-    assert (oracle.batch_normalize(got) == oracle.batch_normalize(oracle.scalar_mul_fixed(oracle.generator(), k))).all()
+    want = oracle.batch_normalize(oracle.scalar_mul_fixed(oracle.generator(), k))
+    for w in (4, 7):  # both window widths of the fixed-base table
+        # the table the device kernel builds, computed here by the oracle: entry e = (j+1) * 2^(w*i) * G
+        nw, per = -(-252 // w), 1 << (w - 1)
+        mult = [(j + 1) << (w * i) for i in range(nw) for j in range(per)] + [1 << (w * nw)]
+        # 2^(w*nw) >= 2^252 is outside multiply()'s 252-bit range: build it as 2^(w*(nw-1)) * G doubled w times
+        sc = scalar_bytes(*[m if m < (1 << 252) else 1 << (w * (nw - 1)) for m in mult])
+        ext = oracle.scalar_mul_fixed(oracle.generator(), sc)
+        top = ext[-1:]
+        for _ in range(w):
+            top = oracle.ext_double(top)
+        ext[-1] = top[0]
+        tbl = oracle.affine_to_niels(oracle.batch_normalize(ext)).view(np.uint32).reshape(-1, 24)
+        assert tbl.size == emul.table_words(w)
+        for first in (0, per - 1, (nw // 2) * per + 3, nw * per - 2):  # incl. the top-carry entry
+            got = emul.fixed_entries(oracle.generator(), w, first, 3)
+            assert (got == tbl[first:first + 3][:len(got)]).all(), (w, first)
+        assert (oracle.batch_normalize(emul.smul_fixed(tbl, k, w)) == want).all(), w
 
 
 def test_emulated_sqrt_and_decode(built, oracle):
