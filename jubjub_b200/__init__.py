@@ -6,3 +6,5 @@ from .engine import FQ, FR, DeviceArray, Engine, JubjubError, default_engine  # 
 from .sharding import equal_shards, gather_offsets, shard_range  # noqa: F401
 
 __all__ = ["Engine", "DeviceArray", "JubjubError", "default_engine", "FQ", "FR", "LIB_PATH"]
+
+from . import types  # noqa: E402,F401  (reference-style batch types: jubjub_b200.types.Fq, ExtendedPoint, ...)

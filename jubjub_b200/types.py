@@ -1,0 +1,402 @@
+"""Batch-valued mirrors of the reference's public types, so that host code and the parity tests
+read like the reference's own (`src/lib.rs`, `src/fr.rs`): every object holds a *batch* of n values
+and every operator acts element-wise on the GPU through the C ABI.
+
+    p = ExtendedPoint.from_affine(AffinePoint.generator(n)).mul_by_cofactor()
+    assert (p * a) * b == p * (a * b)                       # src/lib.rs:1505-1527
+    enc = batch_normalize(p * k).to_bytes()                 # src/lib.rs:1084-1107, 455-464
+
+Names, argument meaning and failure behaviour follow the reference: `invert()` / `from_bytes()`
+return `(value, is_some)` like `CtOption` (src/fr.rs:268-292, 438-540), a length mismatch raises
+(`assert_eq!`, src/lib.rs:841), `ExtendedPoint.__eq__` is projective equality (src/lib.rs:153-163),
+scalar multiplication takes `Fr` in Montgomery form and ignores nothing but what `Fr` cannot hold.
+There is no CPU arithmetic here: without a B200 the engine constructor raises.
+"""
+import numpy as np
+
+from . import _lib as L
+from .engine import default_engine
+
+_GEN_RAW = (0x62EDCBB8BF3787C88B0F03DDD60A8187CAF55D1B29BF81AFE4B3D35DF1A7ADFE, 11)  # src/lib.rs:1380-1396
+_EDWARDS_D2_RAW = 0x552631CE97F45691EBFB240FCD7AFFA8525AFEDA6EAF3A4C020CBFADAC687D62  # 2d, src/lib.rs:407-412
+
+
+def _limbs(x):
+    return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+
+
+class _Field:
+    """Common implementation of Fq / Fr batches; `limbs` is (n, 4) uint64 Montgomery form."""
+
+    _name = None
+
+    def __init__(self, limbs, engine=None):
+        self.limbs = np.ascontiguousarray(limbs, dtype=np.uint64).reshape(-1, 4)
+        self.eng = engine or default_engine()
+
+    def __len__(self):
+        return len(self.limbs)
+
+    # ---- constructors (src/fr.rs:246-349) ----------------------------------------------------
+    @classmethod
+    def zero(cls, n=1, engine=None):
+        return cls(np.zeros((n, 4), dtype=np.uint64), engine)
+
+    @classmethod
+    def from_raw(cls, values, engine=None):
+        """from_raw([u64; 4]) for each Python int / limb list: the integer's residue in Montgomery form."""
+        eng = engine or default_engine()
+        raw = np.array([_limbs(v) if isinstance(v, int) else list(v) for v in values], dtype=np.uint64).reshape(-1, 4)
+        wide = np.zeros((len(raw), 64), dtype=np.uint8)
+        wide[:, :32] = raw.view(np.uint8).reshape(-1, 32)
+        return cls(eng.fe_from_bytes_wide(cls._name, wide), eng)  # d0*R2 + 0*R3 == from_raw(d0)
+
+    @classmethod
+    def one(cls, n=1, engine=None):
+        return cls.from_raw([1] * n, engine)
+
+    @classmethod
+    def from_u64(cls, values, engine=None):
+        return cls.from_raw([int(v) for v in np.atleast_1d(values)], engine)
+
+    @classmethod
+    def from_bytes(cls, b, engine=None):
+        """-> (value, is_some); is_some[i] = 0 when the encoding is not canonical (src/fr.rs:268-292)."""
+        eng = engine or default_engine()
+        v, ok = eng.fe_from_bytes(cls._name, np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32))
+        return cls(v, eng), ok
+
+    @classmethod
+    def from_bytes_wide(cls, b, engine=None):
+        eng = engine or default_engine()
+        return cls(eng.fe_from_bytes_wide(cls._name, np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 64)), eng)
+
+    # ---- arithmetic ------------------------------------------------------------------------------
+    def _chk(self, o):
+        if not isinstance(o, type(self)):
+            raise TypeError(f"{type(self).__name__} op {type(o).__name__}")
+        return o.limbs
+
+    def __add__(self, o):
+        return type(self)(self.eng.fe_add(self._name, self.limbs, self._chk(o)), self.eng)
+
+    def __sub__(self, o):
+        return type(self)(self.eng.fe_sub(self._name, self.limbs, self._chk(o)), self.eng)
+
+    def __mul__(self, o):
+        if isinstance(o, type(self)):
+            return type(self)(self.eng.fe_mul(self._name, self.limbs, o.limbs), self.eng)
+        return NotImplemented
+
+    def __neg__(self):
+        return type(self)(self.eng.fe_neg(self._name, self.limbs), self.eng)
+
+    def square(self):
+        return type(self)(self.eng.fe_square(self._name, self.limbs), self.eng)
+
+    def double(self):
+        return type(self)(self.eng.fe_double(self._name, self.limbs), self.eng)
+
+    def invert(self):
+        """-> (inverse, is_some) (src/fr.rs:438-540)."""
+        v, ok = self.eng.fe_invert(self._name, self.limbs)
+        return type(self)(v, self.eng), ok
+
+    def to_bytes(self):
+        return self.eng.fe_to_bytes(self._name, self.limbs)
+
+    def __eq__(self, o):
+        return isinstance(o, type(self)) and self.limbs.shape == o.limbs.shape and bool((self.limbs == o.limbs).all())
+
+    __hash__ = None
+
+    def __getitem__(self, i):
+        return type(self)(self.limbs[i].reshape(-1, 4), self.eng)
+
+    def __repr__(self):  # Debug prints the canonical value big-endian (src/fr.rs:25-40)
+        b = self.to_bytes()
+        return f"{type(self).__name__}[" + ", ".join("0x" + bytes(r)[::-1].hex() for r in b[:4]) + (", ...]" if len(b) > 4 else "]")
+
+
+class Fq(_Field):
+    """jubjub::Fq = bls12_381::Scalar (src/lib.rs:62)."""
+    _name = "fq"
+
+
+class Fr(_Field):
+    """jubjub::Fr (src/fr.rs:23)."""
+    _name = "fr"
+
+
+class AffineNielsPoint:
+    """(v+u, v-u, u*v*2d) (src/lib.rs:255-259); `data` is (n, 12) uint64."""
+
+    def __init__(self, data, engine=None):
+        self.data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 12)
+        self.eng = engine or default_engine()
+
+    @classmethod
+    def identity(cls, n=1, engine=None):
+        return AffinePoint.identity(n, engine).to_niels()
+
+    def __len__(self):
+        return len(self.data)
+
+    def to_affine(self):
+        """(u, v) = ((vpu - vmu)/2, (vpu + vmu)/2)."""
+        vpu, vmu = Fq(self.data[:, 0:4], self.eng), Fq(self.data[:, 4:8], self.eng)
+        half = _half(len(self), self.eng)
+        return AffinePoint.from_raw_unchecked((vpu - vmu) * half, (vpu + vmu) * half)
+
+    def __mul__(self, k):
+        """`&AffineNielsPoint * &Fr` (src/lib.rs:304-310)."""
+        if not isinstance(k, Fr):
+            return NotImplemented
+        return self.to_affine().to_extended() * k
+
+    def multiply_bits(self, by):
+        return self.to_affine().to_extended().multiply_bits(by)
+
+
+def _half(n, eng):
+    inv, _ = Fq.from_raw([2] * n, eng).invert()
+    return inv
+
+
+class ExtendedNielsPoint:
+    """(V+U, V-U, Z, T1*T2*2d) (src/lib.rs:327-332); `data` is (n, 16) uint64."""
+
+    def __init__(self, data, engine=None):
+        self.data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 16)
+        self.eng = engine or default_engine()
+
+    @classmethod
+    def identity(cls, n=1, engine=None):
+        return ExtendedPoint.identity(n, engine).to_niels()
+
+    def __len__(self):
+        return len(self.data)
+
+    def to_extended(self):
+        """An ExtendedPoint whose to_niels() is this value: U = (vpu - vmu)/2, V = (vpu + vmu)/2, Z = z,
+        T1 = t2d / 2d, T2 = 1 (so that T1*T2*2d = t2d)."""
+        n = len(self)
+        vpu, vmu = Fq(self.data[:, 0:4], self.eng), Fq(self.data[:, 4:8], self.eng)
+        z, t2d = Fq(self.data[:, 8:12], self.eng), Fq(self.data[:, 12:16], self.eng)
+        half = _half(n, self.eng)
+        d2 = Fq.from_raw([_EDWARDS_D2_RAW] * n, self.eng)
+        inv_d2, _ = d2.invert()
+        u, v, t1 = (vpu - vmu) * half, (vpu + vmu) * half, t2d * inv_d2
+        return ExtendedPoint(np.concatenate([u.limbs, v.limbs, z.limbs, t1.limbs, Fq.one(n, self.eng).limbs], axis=1),
+                             self.eng)
+
+    def __mul__(self, k):
+        """`&ExtendedNielsPoint * &Fr` (src/lib.rs:388-394)."""
+        if not isinstance(k, Fr):
+            return NotImplemented
+        return self.to_extended() * k
+
+    def multiply_bits(self, by):
+        return self.to_extended().multiply_bits(by)
+
+
+class AffinePoint:
+    """(u, v) (src/lib.rs:81-84); `data` is (n, 8) uint64 Montgomery limbs."""
+
+    def __init__(self, data, engine=None):
+        self.data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 8)
+        self.eng = engine or default_engine()
+
+    def __len__(self):
+        return len(self.data)
+
+    @classmethod
+    def from_raw_unchecked(cls, u, v):
+        assert isinstance(u, Fq) and isinstance(v, Fq) and len(u) == len(v)
+        return cls(np.concatenate([u.limbs, v.limbs], axis=1), u.eng)
+
+    @classmethod
+    def identity(cls, n=1, engine=None):
+        return cls.from_raw_unchecked(Fq.zero(n, engine), Fq.one(n, engine))
+
+    @classmethod
+    def generator(cls, n=1, engine=None):
+        return cls.from_raw_unchecked(Fq.from_raw([_GEN_RAW[0]] * n, engine), Fq.from_raw([_GEN_RAW[1]] * n, engine))
+
+    @classmethod
+    def batch_from_bytes(cls, b, engine=None):
+        """-> (points, is_some) (src/lib.rs:541-627)."""
+        eng = engine or default_engine()
+        pts, ok = eng.batch_from_bytes(np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32))
+        return cls(pts, eng), ok
+
+    from_bytes = batch_from_bytes
+
+    @classmethod
+    def from_bytes_pre_zip216_compatibility(cls, b, engine=None):
+        eng = engine or default_engine()
+        pts, ok = eng.batch_from_bytes(np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32), zip216=False)
+        return cls(pts, eng), ok
+
+    def get_u(self):
+        return Fq(self.data[:, :4], self.eng)
+
+    def get_v(self):
+        return Fq(self.data[:, 4:], self.eng)
+
+    def to_bytes(self):
+        return self.eng.affine_to_bytes(self.data)
+
+    def to_extended(self):
+        return ExtendedPoint.from_affine(self)
+
+    def to_niels(self):
+        return AffineNielsPoint(self.eng.affine_to_niels(self.data), self.eng)
+
+    def __neg__(self):
+        return AffinePoint.from_raw_unchecked(-self.get_u(), self.get_v())
+
+    def __eq__(self, o):
+        return isinstance(o, AffinePoint) and self.data.shape == o.data.shape and bool((self.data == o.data).all())
+
+    __hash__ = None
+
+    def __mul__(self, k):
+        """`&AffinePoint * &Fr` (src/lib.rs:1109-1115); one shared base uses the fixed-base kernel."""
+        if not isinstance(k, Fr):
+            return NotImplemented
+        if len(self) == 1:
+            return ExtendedPoint(self.eng.scalar_mul_fixed(self.data, k.limbs, scalar_mont=True), self.eng)
+        return self.to_extended() * k
+
+    def mul_by_cofactor(self):
+        return self.to_extended().mul_by_cofactor()
+
+    def is_identity(self):
+        return self.to_extended().is_identity()
+
+    def is_small_order(self):
+        return self.to_extended().is_small_order()
+
+    def is_torsion_free(self):
+        return self.to_extended().is_torsion_free()
+
+    def is_prime_order(self):
+        return self.to_extended().is_prime_order()
+
+
+class ExtendedPoint:
+    """(U, V, Z, T1, T2) (src/lib.rs:139-145); `data` is (n, 20) uint64 Montgomery limbs."""
+
+    def __init__(self, data, engine=None):
+        self.data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 20)
+        self.eng = engine or default_engine()
+
+    def __len__(self):
+        return len(self.data)
+
+    @classmethod
+    def from_affine(cls, a):
+        one = Fq.one(len(a), a.eng).limbs
+        return cls(np.concatenate([a.data, one, a.data], axis=1), a.eng)  # (u, v, 1, u, v), src/lib.rs:214-226
+
+    @classmethod
+    def identity(cls, n=1, engine=None):
+        return cls.from_affine(AffinePoint.identity(n, engine))
+
+    def _same(self, o):
+        if len(o) != len(self):
+            raise ValueError(f"length mismatch: {len(self)} != {len(o)}")  # assert_eq!, src/lib.rs:841
+
+    def double(self):
+        return ExtendedPoint(self.eng.point_double(self.data), self.eng)
+
+    def to_niels(self):
+        return ExtendedNielsPoint(self.eng.point_to_niels(self.data), self.eng)
+
+    def _addsub(self, o, subtract):
+        self._same(o)
+        if isinstance(o, ExtendedPoint):
+            return ExtendedPoint(self.eng.point_add(self.data, o.data, subtract=subtract), self.eng)
+        if isinstance(o, ExtendedNielsPoint):
+            return ExtendedPoint(self.eng.point_add_niels(self.data, o.data, subtract=subtract), self.eng)
+        if isinstance(o, AffineNielsPoint):
+            return ExtendedPoint(self.eng.point_add_affine_niels(self.data, o.data, subtract=subtract), self.eng)
+        if isinstance(o, AffinePoint):  # src/lib.rs:1012-1028
+            return self._addsub(o.to_niels(), subtract)
+        return NotImplemented
+
+    def __add__(self, o):
+        return self._addsub(o, False)
+
+    def __sub__(self, o):
+        return self._addsub(o, True)
+
+    def __neg__(self):  # (-U, V, Z, -T1, T2), src/lib.rs:196-210
+        d = self.data.copy()
+        d[:, 0:4] = self.eng.fe_neg("fq", self.data[:, 0:4])
+        d[:, 12:16] = self.eng.fe_neg("fq", self.data[:, 12:16])
+        return ExtendedPoint(d, self.eng)
+
+    def __mul__(self, k):
+        """`&ExtendedPoint * &Fr` (src/lib.rs:873-879)."""
+        if not isinstance(k, Fr):
+            return NotImplemented
+        self._same(k)
+        return ExtendedPoint(self.eng.scalar_mul(self.data, k.limbs, scalar_mont=True), self.eng)
+
+    def multiply_bits(self, by):
+        """[k]P for 32 little-endian bytes per point, top four bits ignored (src/lib.rs:381-385)."""
+        return ExtendedPoint(self.eng.scalar_mul(self.data, np.ascontiguousarray(by, dtype=np.uint8).reshape(-1, 32)), self.eng)
+
+    def mul_by_cofactor(self):
+        return self.double().double().double()
+
+    def is_identity(self):
+        return self.eng.is_identity(self.data)
+
+    def is_small_order(self):
+        return self.eng.is_small_order(self.data)
+
+    def is_torsion_free(self):
+        return self.eng.is_torsion_free(self.data)
+
+    def is_prime_order(self):
+        return self.is_torsion_free() & (1 - self.is_identity())
+
+    def to_affine(self):
+        return AffinePoint(self.eng.batch_normalize(self.data), self.eng)
+
+    def __eq__(self, o):
+        """(u/z, v/z) == (u'/z', v'/z') via u*z' == u'*z and v*z' == v'*z (src/lib.rs:153-163)."""
+        if not isinstance(o, ExtendedPoint) or len(o) != len(self):
+            return False
+        m = lambda a, b: self.eng.fe_mul("fq", np.ascontiguousarray(a), np.ascontiguousarray(b))  # noqa: E731
+        s, t = self.data, o.data
+        return bool((m(s[:, 0:4], t[:, 8:12]) == m(t[:, 0:4], s[:, 8:12])).all()
+                    and (m(s[:, 4:8], t[:, 8:12]) == m(t[:, 4:8], s[:, 8:12])).all())
+
+    __hash__ = None
+
+    def __getitem__(self, i):
+        return ExtendedPoint(self.data[i].reshape(-1, 20), self.eng)
+
+
+# ---- free functions ---------------------------------------------------------------------------------
+def batch_normalize(points):
+    """jubjub::batch_normalize (src/lib.rs:1084-1107): ExtendedPoint batch -> AffinePoint batch."""
+    return points.to_affine()
+
+
+def batch_mul(points, scalars):
+    """New batch entry point: points[i] * scalars[i] (ExtendedPoint x Fr)."""
+    return points * scalars
+
+
+def batch_add(p, q):
+    """New batch entry point: p[i] + q[i]."""
+    return p + q
+
+
+__all__ = ["Fq", "Fr", "AffinePoint", "ExtendedPoint", "AffineNielsPoint", "ExtendedNielsPoint", "batch_normalize",
+           "batch_mul", "batch_add", "L"]
