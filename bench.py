@@ -197,7 +197,16 @@ def main():
             # scalar-mul kernel then stores each result into all of them over NVLink (no ncclAllGather)
             handles = [None] * world
             dist.all_gather_object(handles, eng.ipc_export(out_all))
-            eng.set_peer_outputs([out_all.ptr if r == rank else eng.ipc_open(handles[r]) for r in range(world)])
+            try:
+                ptrs, ok = [out_all.ptr if r == rank else eng.ipc_open(handles[r]) for r in range(world)], 1
+            except jj.JubjubError:
+                ptrs, ok = None, 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank must be able to map every peer
+            if int(flag.item()) == 1:
+                eng.set_peer_outputs(ptrs)
+            else:
+                gather = "nccl"
 
     def step():
         if world > 1:
