@@ -99,7 +99,6 @@ struct jj_ctx {
     PeerOut peers{};  // peer-mapped gathered-output buffers (fused all-gather); n_peers = 0: off
     int* barrier_word = nullptr;
     uint64_t launches = 0;
-    size_t l2_persist_max = 0, l2_window_max = 0;
     char err[512];
 };
 
@@ -169,21 +168,6 @@ const SmulVariant kVariants[] = {
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
 
-// Keep the window-table scratch resident in L2 (persisting access-policy window on the launch
-// stream): it is rewritten by every scalar-mul, and without the hint the streaming inputs/outputs
-// evict it, turning ~1 KB of table stores per unit into DRAM write-backs (ncu: 3.5x the
-// algorithmic traffic).
-void pin_table_in_l2(jj_ctx* c, cudaStream_t s, char* tbl, size_t bytes) {
-    if (!c->l2_persist_max || !tbl) return;
-    cudaStreamAttrValue v{};
-    v.accessPolicyWindow.base_ptr = tbl;
-    v.accessPolicyWindow.num_bytes = std::min(bytes, c->l2_window_max);
-    v.accessPolicyWindow.hitRatio = bytes <= c->l2_persist_max ? 1.0f : (float)c->l2_persist_max / (float)bytes;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);  // best effort
-}
-
 template <int T, int MB, int TAB>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
     auto kern = k_scalar_mul<T, MB, TAB>;
@@ -194,7 +178,6 @@ int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t*
     } else {
         int32_t rc = ensure(c, tbl, tbl_cap, (size_t)grid * (T / 32) * 32768);
         if (rc) return rc;
-        pin_table_in_l2(c, s, *tbl, (size_t)grid * (T / 32) * 32768);
     }
     a.tbl_scratch = *tbl;
     kern<<<grid, T, smem, s>>>(a);
@@ -210,7 +193,6 @@ int32_t launch_smul_slots(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, siz
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int32_t rc = ensure(c, tbl, tbl_cap, (size_t)grid * (T / 32) * 32768);
     if (rc) return rc;
-    pin_table_in_l2(c, s, *tbl, (size_t)grid * (T / 32) * 32768);
     a.tbl_scratch = *tbl;
     kern<<<grid, T, smem, s>>>(a);
     c->launches++;
@@ -488,11 +470,6 @@ int32_t jj_init(int device, jj_ctx** out) {
         return JJ_ERR_NO_DEVICE;  // sm_100a code only
     }
     c->sm_count = prop.multiProcessorCount;
-    if (prop.persistingL2CacheMaxSize > 0 &&
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize) == cudaSuccess) {
-        c->l2_persist_max = prop.persistingL2CacheMaxSize;
-        c->l2_window_max = prop.accessPolicyMaxWindowSize;
-    }
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < kStages && ok; k++) ok = cudaStreamCreateWithFlags(&c->st[k].stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;

@@ -26,6 +26,49 @@ __device__ __forceinline__ void st_fe(void* p, const fe& r) {
                  "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]), "l"(p)
                  : "memory");
 }
+// L2 eviction hints for the scalar-mul kernels: the per-thread window table is re-read 63 times and
+// rewritten by every unit, so its lines are marked evict-last; the streamed inputs and outputs are
+// marked evict-first so that 352 MB of them per launch do not push the table out to DRAM.
+__device__ __forceinline__ void ld_fe_keep(fe& r, const void* p) {
+    asm volatile("ld.global.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
+                   "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_fe_keep(void* p, const fe& r) {
+    asm volatile("st.global.L2::evict_last.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r.w[0]), "r"(r.w[1]),
+                 "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]), "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_fe_stream(fe& r, const void* p) {
+    asm volatile("ld.global.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
+                   "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_fe_stream(void* p, const fe& r) {
+    asm volatile("st.global.L2::evict_first.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r.w[0]), "r"(r.w[1]),
+                 "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]), "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_ext_stream(ext_point& p, const void* base, size_t i) {
+    const char* b = (const char*)base + i * 160;
+    ld_fe_stream(p.u, b);
+    ld_fe_stream(p.v, b + 32);
+    ld_fe_stream(p.z, b + 64);
+    ld_fe_stream(p.t1, b + 96);
+    ld_fe_stream(p.t2, b + 128);
+}
+__device__ __forceinline__ void st_ext_stream(void* base, size_t i, const ext_point& p) {
+    char* b = (char*)base + i * 160;
+    st_fe_stream(b, p.u);
+    st_fe_stream(b + 32, p.v);
+    st_fe_stream(b + 64, p.z);
+    st_fe_stream(b + 96, p.t1);
+    st_fe_stream(b + 128, p.t2);
+}
 __device__ __forceinline__ void ld_ext(ext_point& p, const void* base, size_t i) {
     const char* b = (const char*)base + i * 160;
     ld_fe(p.u, b);
@@ -226,11 +269,11 @@ struct GmemTable {
     char* base;  // warp slab + lane * 32
     __device__ __forceinline__ void store(int j, const ext_niels& n) {
         char* p = base + (size_t)j * 4 * 1024;
-        st_fe(p, n.vpu); st_fe(p + 1024, n.vmu); st_fe(p + 2048, n.z); st_fe(p + 3072, n.t2d);
+        st_fe_keep(p, n.vpu); st_fe_keep(p + 1024, n.vmu); st_fe_keep(p + 2048, n.z); st_fe_keep(p + 3072, n.t2d);
     }
     __device__ __forceinline__ void load(int j, ext_niels& n) const {
         const char* p = base + (size_t)j * 4 * 1024;
-        ld_fe(n.vpu, p); ld_fe(n.vmu, p + 1024); ld_fe(n.z, p + 2048); ld_fe(n.t2d, p + 3072);
+        ld_fe_keep(n.vpu, p); ld_fe_keep(n.vmu, p + 1024); ld_fe_keep(n.z, p + 2048); ld_fe_keep(n.t2d, p + 3072);
     }
 };
 
@@ -258,9 +301,9 @@ struct SmulArgs {
 __device__ __forceinline__ void smul_store(const SmulArgs& a, size_t i, const ext_point& acc) {
     if (a.peers.n_peers > 0) {
 #pragma unroll 1
-        for (int r = 0; r < a.peers.n_peers; r++) st_ext(a.peers.ptr[r], a.peers.base_unit + i, acc);
+        for (int r = 0; r < a.peers.n_peers; r++) st_ext_stream(a.peers.ptr[r], a.peers.base_unit + i, acc);
     } else {
-        st_ext(a.out, i, acc);
+        st_ext_stream(a.out, i, acc);
     }
 }
 
@@ -272,8 +315,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulAr
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < a.n; i += stride) {
         ext_point P, acc;
         fe k;
-        ld_ext(P, a.points, i);
-        ld_fe(k, a.scalars + i * a.scalar_stride);
+        ld_ext_stream(P, a.points, i);
+        ld_fe_stream(k, a.scalars + i * a.scalar_stride);
         if (a.scalar_mont) fe_to_canonical<FrP>(k, k);  // Fr::to_bytes, src/lib.rs:877
         if (TABLE == TABLE_SMEM) {
             SmemTable t{smem_tbl + (size_t)warp * 2048 + lane};
