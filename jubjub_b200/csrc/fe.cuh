@@ -337,68 +337,21 @@ JJ_DEVICE void mont_mul(fe& r, const fe& a, const fe& b) {
 // a^2 = sum_i a_i B^i (a_i B^i + 2 * sum_{j>i} a_j B^j): row i multiplies a_i by the vector
 // (a_i, 2a_{i+1}, ..., 2a_7) taken from the bit-doubled operand, so only 8 - i products are
 // issued (36 IMAD.WIDE instead of 64; total 36 + 48 = 84 for Fq).  Columns below the first
-// product of a chain only propagate the merge carry (addc).  Because row i already contains
-// the doubled cross terms of later rows, the running total can exceed the 9-word window by
-// one bit; `top` carries that bit into the next row's highest word.  Needs a < 2^255 (true for
-// canonical Fq / Fr), so that the doubled operand has no ninth word.
+// product of a chain only propagate the merge carry (addc).
+//
+// Row i already contains the doubled cross terms of later rows, so the running total is bounded
+// by (2a + m)(B + 1) instead of 2m(B + 1).  It still fits the 9-word window -- and every carry
+// argument of mont_mul still holds -- as long as 2a + m < 2^256 (1 - 2^-32).  That is always true
+// for Fr (3r < 2^254); for Fq it is true for a <= q/2, so larger inputs are squared as q - a
+// (same square), selected by the top limb: one 8-limb subtraction and 8 selects, all ALU work,
+// instead of tracking a 257th bit on the multiplier pipe.  Needs a < m (canonical input).
 template <int I, int J>
 JJ_DEVICE uint32_t sqr_operand(const uint32_t a[8], const uint32_t dw[8]) {
     return J == I ? a[I] : (J == I + 1 ? (dw[J] & 0xfffffffeu) : dw[J]);
 }
-template <class F>
-JJ_DEVICE void redc_row_top(uint32_t E[8], uint32_t O[8], uint32_t& top);
-template <>
-JJ_DEVICE_SPEC void redc_row_top<FqP>(uint32_t E[8], uint32_t O[8], uint32_t& top) {
-    uint32_t e0 = E[0], q, hi, t;
-    sub_cc(q, 0u, e0);
-    subc(hi, q, 0u);
-    add_cc(t, e0, 0xffffffffu);
-    addc_cc(O[0], O[0], e0);
-    addc_cc(O[1], O[1], hi);
-    JJ_MADC_LO_CC_I(O[2], q, FqP::M3, O[2]);
-    JJ_MADC_HI_CC_I(O[3], q, FqP::M3, O[3]);
-    JJ_MADC_LO_CC_I(O[4], q, FqP::M5, O[4]);
-    JJ_MADC_HI_CC_I(O[5], q, FqP::M5, O[5]);
-    JJ_MADC_LO_CC_I(O[6], q, FqP::M7, O[6]);
-    JJ_MADC_HI_CC_I(O[7], q, FqP::M7, O[7]);
-    addc(top, top, 0u);
-    JJ_MAD_LO_CC_I(E[2], q, FqP::M2, E[2]);
-    JJ_MADC_HI_CC_I(E[3], q, FqP::M2, E[3]);
-    JJ_MADC_LO_CC_I(E[4], q, FqP::M4, E[4]);
-    JJ_MADC_HI_CC_I(E[5], q, FqP::M4, E[5]);
-    JJ_MADC_LO_CC_I(E[6], q, FqP::M6, E[6]);
-    JJ_MADC_HI_CC_I(E[7], q, FqP::M6, E[7]);
-    addc_cc(O[7], O[7], 0u);
-    addc(top, top, 0u);
-    E[0] = 0;
-    (void)t;
-}
-template <>
-JJ_DEVICE_SPEC void redc_row_top<FrP>(uint32_t E[8], uint32_t O[8], uint32_t& top) {
-    uint32_t q = E[0] * FrP::INV;
-    JJ_MAD_LO_CC_I(O[0], q, FrP::M1, O[0]);
-    JJ_MADC_HI_CC_I(O[1], q, FrP::M1, O[1]);
-    JJ_MADC_LO_CC_I(O[2], q, FrP::M3, O[2]);
-    JJ_MADC_HI_CC_I(O[3], q, FrP::M3, O[3]);
-    JJ_MADC_LO_CC_I(O[4], q, FrP::M5, O[4]);
-    JJ_MADC_HI_CC_I(O[5], q, FrP::M5, O[5]);
-    JJ_MADC_LO_CC_I(O[6], q, FrP::M7, O[6]);
-    JJ_MADC_HI_CC_I(O[7], q, FrP::M7, O[7]);
-    addc(top, top, 0u);
-    JJ_MAD_LO_CC_I(E[0], q, FrP::M0, E[0]);
-    JJ_MADC_HI_CC_I(E[1], q, FrP::M0, E[1]);
-    JJ_MADC_LO_CC_I(E[2], q, FrP::M2, E[2]);
-    JJ_MADC_HI_CC_I(E[3], q, FrP::M2, E[3]);
-    JJ_MADC_LO_CC_I(E[4], q, FrP::M4, E[4]);
-    JJ_MADC_HI_CC_I(E[5], q, FrP::M4, E[5]);
-    JJ_MADC_LO_CC_I(E[6], q, FrP::M6, E[6]);
-    JJ_MADC_HI_CC_I(E[7], q, FrP::M6, E[7]);
-    addc_cc(O[7], O[7], 0u);
-    addc(top, top, 0u);
-}
 // Row I >= 1 of the squaring.  Same column bookkeeping as mul_row.
 template <int I>
-JJ_DEVICE void sqr_row(uint32_t E[8], uint32_t O[8], uint32_t& top, const uint32_t a[8], const uint32_t dw[8]) {
+JJ_DEVICE void sqr_row(uint32_t E[8], uint32_t O[8], const uint32_t a[8], const uint32_t dw[8]) {
     const uint32_t bi = a[I];
     add_cc(E[0], E[0], O[1]);
     // odd columns J = 1, 3, 5, 7 -> O pairs (0,1), (2,3), (4,5), (6,7), sliding down two words
@@ -424,8 +377,7 @@ JJ_DEVICE void sqr_row(uint32_t E[8], uint32_t O[8], uint32_t& top, const uint32
         addc_cc(O[5], O[7], 0u);
     }
     madc_lo_cc(O[6], sqr_operand<I, 7>(a, dw), bi, 0u);
-    madc_hi_cc(O[7], sqr_operand<I, 7>(a, dw), bi, top);
-    addc(top, 0u, 0u);
+    madc_hi(O[7], sqr_operand<I, 7>(a, dw), bi, 0u);
     // even columns J = 0, 2, 4, 6 -> E pairs, in place; the chain starts at the first J >= I
     if (I <= 6) {
         if (I <= 0) {
@@ -454,20 +406,41 @@ JJ_DEVICE void sqr_row(uint32_t E[8], uint32_t O[8], uint32_t& top, const uint32
             madc_lo_cc(E[6], sqr_operand<I, 6>(a, dw), bi, E[6]);
         }
         madc_hi_cc(E[7], sqr_operand<I, 6>(a, dw), bi, E[7]);
-        addc_cc(O[7], O[7], 0u);
-        addc(top, top, 0u);
+        addc(O[7], O[7], 0u);
     }
+}
+// x = a or m - a, whichever has its top limb <= m7 / 2 (then 2x + m < 2^256 (1 - 2^-32)).
+template <class F>
+JJ_DEVICE void sqr_fold(uint32_t x[8], const fe& a) {
+    if (3.0 * (double)F::M7 < 4294967295.0 * 0.999) {  // 3m < 2^256 already: nothing to do (Fr)
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = a.w[i];
+        return;
+    }
+    uint32_t n[8];
+    sub_cc(n[0], F::M0, a.w[0]);
+    subc_cc(n[1], F::M1, a.w[1]);
+    subc_cc(n[2], F::M2, a.w[2]);
+    subc_cc(n[3], F::M3, a.w[3]);
+    subc_cc(n[4], F::M4, a.w[4]);
+    subc_cc(n[5], F::M5, a.w[5]);
+    subc_cc(n[6], F::M6, a.w[6]);
+    subc(n[7], F::M7, a.w[7]);
+    const bool big = a.w[7] > (F::M7 >> 1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = big ? n[i] : a.w[i];
 }
 template <class F>
 JJ_DEVICE void mont_sqr(fe& r, const fe& a) {
-    uint32_t X[8], Y[8], dw[8], top = 0;
+    uint32_t X[8], Y[8], dw[8], x[8];
+    sqr_fold<F>(x, a);
     dw[0] = 0;
 #pragma unroll
-    for (int j = 1; j < 8; j++) dw[j] = (a.w[j] << 1) | (a.w[j - 1] >> 31);
-    {   // row 0: a_0 * (a_0, 2a_1, ..., 2a_7), nothing accumulated yet
-        const uint32_t b0 = a.w[0];
+    for (int j = 1; j < 8; j++) dw[j] = (x[j] << 1) | (x[j - 1] >> 31);
+    {   // row 0: x_0 * (x_0, 2x_1, ..., 2x_7), nothing accumulated yet
+        const uint32_t b0 = x[0];
         uint64_t e, o;
-        e = (uint64_t)a.w[0] * b0;                 X[0] = (uint32_t)e; X[1] = (uint32_t)(e >> 32);
+        e = (uint64_t)x[0] * b0;                   X[0] = (uint32_t)e; X[1] = (uint32_t)(e >> 32);
         o = (uint64_t)(dw[1] & 0xfffffffeu) * b0;  Y[0] = (uint32_t)o; Y[1] = (uint32_t)(o >> 32);
         e = (uint64_t)dw[2] * b0;                  X[2] = (uint32_t)e; X[3] = (uint32_t)(e >> 32);
         o = (uint64_t)dw[3] * b0;                  Y[2] = (uint32_t)o; Y[3] = (uint32_t)(o >> 32);
@@ -476,22 +449,22 @@ JJ_DEVICE void mont_sqr(fe& r, const fe& a) {
         e = (uint64_t)dw[6] * b0;                  X[6] = (uint32_t)e; X[7] = (uint32_t)(e >> 32);
         o = (uint64_t)dw[7] * b0;                  Y[6] = (uint32_t)o; Y[7] = (uint32_t)(o >> 32);
     }
-    redc_row_top<F>(X, Y, top);
-    sqr_row<1>(Y, X, top, a.w, dw);
-    redc_row_top<F>(Y, X, top);
-    sqr_row<2>(X, Y, top, a.w, dw);
-    redc_row_top<F>(X, Y, top);
-    sqr_row<3>(Y, X, top, a.w, dw);
-    redc_row_top<F>(Y, X, top);
-    sqr_row<4>(X, Y, top, a.w, dw);
-    redc_row_top<F>(X, Y, top);
-    sqr_row<5>(Y, X, top, a.w, dw);
-    redc_row_top<F>(Y, X, top);
-    sqr_row<6>(X, Y, top, a.w, dw);
-    redc_row_top<F>(X, Y, top);
-    sqr_row<7>(Y, X, top, a.w, dw);
-    redc_row_top<F>(Y, X, top);
-    mont_finish<F>(r, Y, X);  // top is 0 here: the final value is < 2m < 2^256
+    redc_row<F>(X, Y);
+    sqr_row<1>(Y, X, x, dw);
+    redc_row<F>(Y, X);
+    sqr_row<2>(X, Y, x, dw);
+    redc_row<F>(X, Y);
+    sqr_row<3>(Y, X, x, dw);
+    redc_row<F>(Y, X);
+    sqr_row<4>(X, Y, x, dw);
+    redc_row<F>(X, Y);
+    sqr_row<5>(Y, X, x, dw);
+    redc_row<F>(Y, X);
+    sqr_row<6>(X, Y, x, dw);
+    redc_row<F>(X, Y);
+    sqr_row<7>(Y, X, x, dw);
+    redc_row<F>(Y, X);
+    mont_finish<F>(r, Y, X);
 }
 
 // Montgomery form -> canonical integer: one reduction of (a, 0), i.e. a * 1 (src/fr.rs:296-308).
