@@ -122,7 +122,7 @@ def cpu_baseline(sample_points, sample_scalars, cores):
     return len(sample_points) / t, t
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit=print):
     """Reference arm: the reference algorithm (C restatement, oracle/) on all host cores."""
     if rank != 0:
         return
@@ -143,7 +143,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     desc = f"{sample} of 2^{LOG_N} units per step (first {sample} of the same streams), {cores} threads"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (4x64 Montgomery)",
@@ -165,8 +165,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Keep stdout to the single JSON line: anything native libraries print to fd 1 while the bench runs
+    # (e.g. NCCL's version banner) is sent to stderr; the JSON goes to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line, flush=True)
+
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -342,7 +353,7 @@ def main():
                          "single_thread": {"scalar_muls_per_s": cpu_1t, "fq_muls_per_s": cpu_fq,
                                            "sample": "2048 scalar-muls; 1e7 dependent Fq muls, best of 3"}},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
