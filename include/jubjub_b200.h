@@ -117,6 +117,11 @@ int32_t jj_fr_double(jj_ctx* ctx, const void* a, void* out, size_t n, uint32_t f
 /* Fr::invert src/fr.rs:438-540; ok[i] = 0 and out[i] = 0 for a[i] = 0 (CtOption::none) */
 int32_t jj_fq_invert(jj_ctx* ctx, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags);
 int32_t jj_fr_invert(jj_ctx* ctx, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags);
+/* Fr::sqrt src/fr.rs:384-399 (a^((r+1)/4)); Fq::sqrt = [ext] bls12_381::Scalar::sqrt (Tonelli-Shanks, call sites
+ * src/lib.rs:515, 603).  ok[i] = 0 and out[i] = 0 for a non-residue.  Which of the two roots is returned is
+ * not part of the contract (callers fix the sign from the parity, src/lib.rs:518-520): out[i]^2 == a[i]. */
+int32_t jj_fq_sqrt(jj_ctx* ctx, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags);
+int32_t jj_fr_sqrt(jj_ctx* ctx, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags);
 /* Fr::to_bytes src/fr.rs:296-308: Montgomery limbs -> 32 canonical LE bytes */
 int32_t jj_fq_to_bytes(jj_ctx* ctx, const void* a, void* out32, size_t n, uint32_t flags);
 int32_t jj_fr_to_bytes(jj_ctx* ctx, const void* a, void* out32, size_t n, uint32_t flags);

@@ -44,7 +44,7 @@ PROTOTYPES = {
     "jj_fq_sub": _BINARY, "jj_fr_sub": _BINARY,
     "jj_fq_square": _UNARY, "jj_fr_square": _UNARY, "jj_fq_neg": _UNARY, "jj_fr_neg": _UNARY,
     "jj_fq_double": _UNARY, "jj_fr_double": _UNARY,
-    "jj_fq_invert": _WITH_OK, "jj_fr_invert": _WITH_OK,
+    "jj_fq_invert": _WITH_OK, "jj_fr_invert": _WITH_OK, "jj_fq_sqrt": _WITH_OK, "jj_fr_sqrt": _WITH_OK,
     "jj_fq_to_bytes": _UNARY, "jj_fr_to_bytes": _UNARY,
     "jj_fq_from_bytes": _WITH_OK, "jj_fr_from_bytes": _WITH_OK,
     "jj_fq_from_bytes_wide": _UNARY, "jj_fr_from_bytes_wide": _UNARY,

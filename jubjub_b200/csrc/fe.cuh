@@ -543,6 +543,21 @@ JJ_DEVICE void fe_invert(fe& r, const fe& a) {
 // Square root in Fq ([ext] bls12_381::Scalar::sqrt; call sites src/lib.rs:515, :603): Tonelli-Shanks
 // with q - 1 = 2^32 * T.  Returns false for a non-residue.  Which root comes back does not matter to
 // the callers on this path: the sign is fixed from the parity afterwards (src/lib.rs:518-520).
+// Fr::sqrt (src/fr.rs:384-399): r = 3 (mod 4), so the candidate root is a^((r+1)/4); Some iff it squares to a.
+struct ExpFrSqrt {
+    static constexpr int NW = 8;
+    JJ_CONST_FN uint32_t word(int i) {
+        constexpr uint32_t t[8] = {0xb5bdcb2eu, 0xb425c397u, 0xf3320420u, 0x299a0824u, 0x404d0ec0u, 0x4199cec0u, 0x994cebeau, 0x039f6d3au};
+        return t[i];
+    }
+};
+JJ_DEVICE bool fr_sqrt(fe& r, const fe& a) {
+    fe s, s2;
+    fe_pow_const<FrP, ExpFrSqrt>(s, a);
+    mont_sqr<FrP>(s2, s);
+    r = s;
+    return fe_eq(s2, a);
+}
 JJ_DEVICE bool fq_sqrt(fe& r, const fe& a) {
     if (fe_is_zero(a)) {
         fe_set_zero(r);

@@ -319,7 +319,7 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
 template <class F, int OP>
 int32_t fe_launch(jj_ctx* c, cudaStream_t s, bool canon, const char* a, const char* b, char* out, uint8_t* ok, size_t n,
                   uint64_t seed, size_t first) {
-    int grid = grid_for(c, n, 256, OP == FE_INV ? 4 : 8);
+    int grid = grid_for(c, n, 256, (OP == FE_INV || OP == FE_SQRT) ? 4 : 8);
     if (canon)
         k_fe_op<F, OP, true><<<grid, 256, 0, s>>>(a, b, out, ok, n, seed, first);
     else
@@ -643,6 +643,12 @@ int32_t jj_fq_invert(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n,
 }
 int32_t jj_fr_invert(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
     return fe_with_ok<FrP, FE_INV>(c, a, out, ok, n, flags);
+}
+int32_t jj_fq_sqrt(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
+    return fe_with_ok<FqP, FE_SQRT>(c, a, out, ok, n, flags);
+}
+int32_t jj_fr_sqrt(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
+    return fe_with_ok<FrP, FE_SQRT>(c, a, out, ok, n, flags);
 }
 int32_t jj_fq_to_bytes(jj_ctx* c, const void* a, void* out, size_t n, uint32_t flags) {
     return fe_binary<FqP, FE_TO_BYTES>(c, a, nullptr, out, n, flags & ~JJ_CANON);

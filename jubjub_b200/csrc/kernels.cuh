@@ -89,7 +89,7 @@ __device__ __forceinline__ void st_ext(void* base, size_t i, const ext_point& p)
 // ---- field batches ------------------------------------------------------------------------
 enum FeOp {
     FE_MUL = 0, FE_SQR, FE_ADD, FE_SUB, FE_NEG, FE_DBL, FE_INV, FE_TO_BYTES, FE_FROM_BYTES,
-    FE_FROM_WIDE, FE_STREAM
+    FE_FROM_WIDE, FE_STREAM, FE_SQRT
 };
 
 __device__ __forceinline__ uint64_t splitmix_at(uint64_t seed, uint64_t idx) {
@@ -157,6 +157,11 @@ __global__ void __launch_bounds__(256) k_fe_op(const char* __restrict__ a, const
                     fe_invert<F>(r, x);
                     break;
                 case FE_TO_BYTES: fe_to_canonical<F>(r, x); break;
+                case FE_SQRT:
+                    fe_set_zero(r);
+                    flag = (F::M0 == FqP::M0) ? fq_sqrt(r, x) : fr_sqrt(r, x);
+                    if (!flag) fe_set_zero(r);
+                    break;
                 default:  // FE_FROM_BYTES
                     flag = fe_is_canonical<F>(x);
                     fe_from_raw<F>(r, x);
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(256) k_fe_op(const char* __restrict__ a, const
         }
         if (CANON && OP != FE_TO_BYTES) fe_to_canonical<F>(r, r);
         st_fe(out + i * 32, r);
-        if ((OP == FE_INV || OP == FE_FROM_BYTES) && ok) ok[i] = flag ? 1 : 0;
+        if ((OP == FE_INV || OP == FE_FROM_BYTES || OP == FE_SQRT) && ok) ok[i] = flag ? 1 : 0;
     }
 }
 

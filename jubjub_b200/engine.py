@@ -154,6 +154,10 @@ class Engine:
         """-> (inverse, ok): ok[i] = 0 and inverse[i] = 0 where a[i] = 0 (CtOption::none)."""
         return self._call(f"jj_{field}_invert", [(a, 4, np.uint64)], 4, flags=flags, ok=True)
 
+    def fe_sqrt(self, field, a):
+        """-> (root, ok): ok[i] = 0 and root[i] = 0 for a non-residue (src/fr.rs:384-399)."""
+        return self._call(f"jj_{field}_sqrt", [(a, 4, np.uint64)], 4, ok=True)
+
     def fe_to_bytes(self, field, a):
         return self._call(f"jj_{field}_to_bytes", [(a, 4, np.uint64)], 32, np.uint8)
 

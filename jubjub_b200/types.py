@@ -102,6 +102,11 @@ class _Field:
         v, ok = self.eng.fe_invert(self._name, self.limbs)
         return type(self)(v, self.eng), ok
 
+    def sqrt(self):
+        """-> (root, is_some) (src/fr.rs:384-399)."""
+        v, ok = self.eng.fe_sqrt(self._name, self.limbs)
+        return type(self)(v, self.eng), ok
+
     def to_bytes(self):
         return self.eng.fe_to_bytes(self._name, self.limbs)
 

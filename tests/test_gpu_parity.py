@@ -83,6 +83,23 @@ def test_field_invert_and_bytes(eng, oracle, which, name):
     assert (got[ok == 1] == want[ok == 1]).all()
 
 
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_field_sqrt(eng, oracle, which, name):
+    """src/fr.rs:1205-1227 (47 non-residues among r-2, r-3, ...) and residue flags vs the oracle for both fields."""
+    a, _ = _field_inputs(oracle, which, 2000)
+    root, ok = eng.fe_sqrt(name, a)
+    _, wok = oracle.fe_sqrt(which, a)
+    assert (ok == wok).all() and 0 < ok.sum() < len(ok)
+    assert (eng.fe_square(name, root[ok == 1]) == a[ok == 1]).all() and (root[ok == 0] == 0).all()
+    if which == FR:
+        sq, vals = fe(K.FR_R_MINUS_2), []
+        for _ in range(100):
+            vals.append(sq[0].copy())
+            sq = eng.fe_sub("fr", sq, oracle.fe_one(FR))
+        _, ok = eng.fe_sqrt("fr", np.array(vals))
+        assert int((ok == 0).sum()) == K.FR_SQRT_NONE_COUNT
+
+
 def test_fr_reference_kats_on_gpu(eng, oracle):
     """src/fr.rs:1045-1099 (LARGEST add/neg/sub), :1024-1034 (wide max), :1758-1776 (a*b==c)."""
     big, one_raw = fe(K.FR_LARGEST), fe([1, 0, 0, 0])
