@@ -1,0 +1,31 @@
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import jubjub_b200 as jj  # noqa: E402
+from scripts.run_smul import SEED0, generator  # noqa: E402
+
+eng = jj.Engine(0)
+n = 700
+a, b = eng.fe_stream("fq", SEED0, n), eng.fe_stream("fq", SEED0 + 1, n)
+for f in ("fq", "fr"):
+    eng.fe_mul(f, a, b); eng.fe_add(f, a, b); eng.fe_sub(f, a, b); eng.fe_square(f, a); eng.fe_neg(f, a)
+    eng.fe_invert(f, a[:64]); eng.fe_sqrt(f, a[:64]); eng.fe_from_bytes(f, eng.fe_to_bytes(f, a))
+g = generator(eng)
+k = eng.fe_to_bytes("fr", eng.fe_stream("fr", SEED0 + 2, n))
+p = eng.scalar_mul_fixed(g, k)
+eng.set_scalar_mul_variant(100); eng.scalar_mul_fixed(g, k[:100]); eng.set_scalar_mul_variant(0)
+q = eng.point_double(p)
+eng.point_add(p, q); eng.point_add_niels(p, eng.point_to_niels(q)); eng.point_add_affine_niels(p, eng.affine_to_niels(eng.batch_normalize(q)))
+for v in (0, 1, 5, 15):
+    eng.set_scalar_mul_variant(v)
+    out = eng.scalar_mul(p, k, output="bytes")
+eng.set_scalar_mul_variant(0)
+pts, ok = eng.batch_from_bytes(out)
+assert ok.all()
+eng.is_torsion_free(p[:64]); eng.is_identity(p); eng.is_small_order(p)
+d = eng.to_device(p); eng.scalar_mul(d, eng.to_device(k), output="affine").download()
+print("sanitize run ok")
