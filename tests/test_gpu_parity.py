@@ -414,3 +414,16 @@ def test_full_size_fixed_base_1m(eng, oracle):
     idx = np.arange(0, n, n // 256)[:256]
     kh = k.download()[idx]
     assert (fixed[idx] == oracle.batch_normalize(oracle.scalar_mul_fixed(gen, kh))).all()
+
+
+def test_scalar_mul_differential_64k(eng, oracle):
+    """65 536 variable-base scalar-muls (projective inputs with z != 1, full-range 256-bit scalar strings so
+    that bits 252..255 are exercised) compared unit by unit with the oracle's reference ladder."""
+    n = 1 << 16
+    t = eng.fe_to_bytes("fr", eng.fe_stream("fr", 7001, n))
+    p = eng.point_double(eng.scalar_mul_fixed(oracle.generator(), t))  # z != 1
+    rng = np.random.default_rng(2024)
+    k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)  # arbitrary top bits: ignored like multiply_bits
+    got = eng.scalar_mul(p, k, output="bytes")
+    want = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(p, k)))
+    assert (got == want).all()
