@@ -49,6 +49,11 @@ struct LocalTable {
     JJ_DEVICE_SPEC void load(int j, ext_niels& n) const { n = t[j]; }
 };
 
+#ifndef JJ_DBL_UNROLL
+#define JJ_DBL_UNROLL 1
+#endif
+constexpr int kDoubleUnroll = JJ_DBL_UNROLL;  // unroll factor of the 4-doubling loop (code size vs register moves)
+
 // acc = [k] P.  `tbl` provides storage for the 8-entry window table.
 template <class Table>
 JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_t k[8], Table& tbl) {
@@ -80,7 +85,7 @@ JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_
     }
 #pragma unroll 1
     for (int i = 62; i >= 0; i--) {
-#pragma unroll 1
+#pragma unroll kDoubleUnroll
         for (int j = 0; j < 4; j++) point_double(acc, acc);
         int d = (int)(K[7] >> 28) - 8;
         shl_256(K, 4);

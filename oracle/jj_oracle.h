@@ -11,7 +11,13 @@
  * reference itself cannot be compiled here.  Every function below cites the
  * reference file:line whose algorithm it follows; Fq follows src/fr.rs with
  * q's constants.  Pinned against the reference's own
- * known-answer tests by tests/test_oracle_kat.py.
+ * known-answer tests by tests/test_oracle_kat.py (every KAT of src/fr.rs:787-1244
+ * and src/lib.rs:1456-1935).  PARITY UNPINNED for one part, stated plainly: the
+ * reference holds no known-answer test for Fq on its own (tests/fq_blackbox.rs is
+ * property-only) and bls12_381 cannot be run here, so Fq limb-level results are
+ * pinned only indirectly -- through the point KATs, which exercise Fq
+ * mul/square/add/sub/invert/sqrt/to_bytes/from_bytes -- plus the big-integer model
+ * (oracle/model.py) and the uniqueness of fully reduced Montgomery limbs.
  *
  * Layout: field element = 4 x u64 little-endian limbs.  Unless a function says
  * "canonical" or "bytes", limbs are in the reference's internal Montgomery form
