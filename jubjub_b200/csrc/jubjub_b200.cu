@@ -164,6 +164,8 @@ const SmulVariant kVariants[] = {
     {448, 1, TABLE_GMEM},      // 19: 14 warps/SM (<= 146 registers)
     {480, 1, TABLE_GMEM},      // 20: 15 warps/SM (<= 136 registers)
     {256, 2, TABLE_GMEM},      // 21: 16 warps/SM in two blocks (<= 128 registers)
+    {576, 1, TABLE_GMEM},      // 22: 18 warps/SM (<= 113 registers, spills)
+    {640, 1, TABLE_GMEM},      // 23: 20 warps/SM (<= 102 registers, spills)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
@@ -232,6 +234,8 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(19, 448, 1, TABLE_GMEM);
         V(20, 480, 1, TABLE_GMEM);
         V(21, 256, 2, TABLE_GMEM);
+        V(22, 576, 1, TABLE_GMEM);
+        V(23, 640, 1, TABLE_GMEM);
         case 15: return launch_smul_slots<512, 1>(c, s, a, tbl, tbl_cap);
         case 16: return launch_smul_slots<384, 1>(c, s, a, tbl, tbl_cap);
         case 17: return launch_smul_slots<544, 1>(c, s, a, tbl, tbl_cap);

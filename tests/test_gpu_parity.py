@@ -187,7 +187,7 @@ def _smul_case(oracle, n):
     return p, k
 
 
-@pytest.mark.parametrize("variant", list(range(0, 22)))
+@pytest.mark.parametrize("variant", list(range(0, 24)))
 def test_scalar_mul_variants(eng, oracle, variant):
     eng.set_scalar_mul_variant(variant)
     try:
