@@ -94,6 +94,14 @@ int32_t jj_memcpy_d2h(jj_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
 int32_t jj_timer_start(jj_ctx* ctx);
 int32_t jj_timer_stop(jj_ctx* ctx, float* elapsed_ms);
 int32_t jj_flush_l2(jj_ctx* ctx); /* overwrites a scratch buffer larger than L2 */
+/* CUDA graphs for launch-bound sequences (many small field/point batches): between jj_graph_begin and
+ * jj_graph_end every call made with JJ_DEVICE_PTRS | JJ_ASYNC is captured on the context's stream instead of
+ * executed; jj_graph_launch replays the whole sequence with one launch (ordered on the stream, jj_sync waits).
+ * Scratch buffers must already exist: run the sequence once eagerly before capturing it. */
+int32_t jj_graph_begin(jj_ctx* ctx);
+int32_t jj_graph_end(jj_ctx* ctx, void** graph_exec);
+int32_t jj_graph_launch(jj_ctx* ctx, void* graph_exec);
+int32_t jj_graph_destroy(jj_ctx* ctx, void* graph_exec);
 /* Measures the chip's IMAD.WIDE.U32 issue rate (instructions x 32 lanes per second) with a
  * register-only kernel: the integer-pipe roofline denominator. */
 int32_t jj_measure_imad_peak(jj_ctx* ctx, double* imad_per_sec);

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "jj_memcpy_h2d": [_vp, _vp, _sz], "jj_memcpy_d2h": [_vp, _vp, _sz],
     "jj_timer_start": [], "jj_timer_stop": [C.POINTER(C.c_float)], "jj_flush_l2": [],
     "jj_measure_imad_peak": [C.POINTER(C.c_double)],
+    "jj_graph_begin": [], "jj_graph_end": [C.POINTER(_vp)], "jj_graph_launch": [_vp], "jj_graph_destroy": [_vp],
     "jj_fq_mul": _BINARY, "jj_fr_mul": _BINARY, "jj_fq_add": _BINARY, "jj_fr_add": _BINARY,
     "jj_fq_sub": _BINARY, "jj_fr_sub": _BINARY,
     "jj_fq_square": _UNARY, "jj_fr_square": _UNARY, "jj_fq_neg": _UNARY, "jj_fr_neg": _UNARY,

@@ -598,6 +598,37 @@ int32_t jj_flush_l2(jj_ctx* c) {
     return JJ_OK;
 }
 
+// ---- CUDA graphs: capture a sequence of JJ_DEVICE_PTRS | JJ_ASYNC calls once, replay it with one launch ----
+int32_t jj_graph_begin(jj_ctx* c) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    return JJ_OK;
+}
+int32_t jj_graph_end(jj_ctx* c, void** graph_exec) {
+    if (!c || !graph_exec) return JJ_ERR_INVALID_ARG;
+    cudaGraph_t g = nullptr;
+    CU(c, cudaStreamEndCapture(c->stream, &g));
+    cudaGraphExec_t e = nullptr;
+    cudaError_t rc = cudaGraphInstantiate(&e, g, 0);
+    cudaGraphDestroy(g);
+    if (rc != cudaSuccess) return fail(c, JJ_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(rc));
+    *graph_exec = e;
+    return JJ_OK;
+}
+int32_t jj_graph_launch(jj_ctx* c, void* graph_exec) {
+    if (!c || !graph_exec) return JJ_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaGraphLaunch((cudaGraphExec_t)graph_exec, c->stream));
+    c->launches++;
+    return JJ_OK;
+}
+int32_t jj_graph_destroy(jj_ctx* c, void* graph_exec) {
+    if (!c || !graph_exec) return JJ_ERR_INVALID_ARG;
+    CU(c, cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return JJ_OK;
+}
+
 int32_t jj_measure_imad_peak(jj_ctx* c, double* imad_per_sec) {
     if (!c || !imad_per_sec) return JJ_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));

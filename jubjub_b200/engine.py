@@ -249,6 +249,25 @@ class Engine:
     def is_small_order(self, p):
         return self._flag("jj_is_small_order", p)
 
+    # ---- CUDA graphs ---------------------------------------------------------------------------
+    def graph_capture(self, fn):
+        """Capture the device-resident, JJ_ASYNC calls made by fn() into a graph; returns a handle for graph_launch.
+        Run fn() once eagerly first so that every scratch buffer exists."""
+        self._check(self.lib.jj_graph_begin(self.ctx))
+        try:
+            fn()
+        finally:
+            g = C.c_void_p()
+            rc = self.lib.jj_graph_end(self.ctx, C.byref(g))
+        self._check(rc)
+        return g
+
+    def graph_launch(self, g):
+        self._check(self.lib.jj_graph_launch(self.ctx, g))
+
+    def graph_destroy(self, g):
+        self._check(self.lib.jj_graph_destroy(self.ctx, g))
+
     # ---- measurement helpers -----------------------------------------------------------------
     def sync(self):
         self._check(self.lib.jj_sync(self.ctx))

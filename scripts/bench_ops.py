@@ -70,6 +70,21 @@ def main():
     flg = eng.empty((n, 1), np.uint8)
     rec("is_torsion_free", timed(eng, lambda: eng._check(eng.lib.jj_is_torsion_free(
         eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS)), reps=2, warm=1), 161)
+    # launch-bound chain: 48 small field batches (n = 4096) eagerly vs replayed as one CUDA graph
+    m = 4096
+    x, y, t2 = eng.fe_stream("fq", 1, m, device=True), eng.fe_stream("fq", 2, m, device=True), eng.empty((m, 4))
+
+    def chain():
+        for _ in range(16):
+            eng.fe_mul("fq", x, y, out=t2, flags=A)
+            eng.fe_add("fq", t2, y, out=t2, flags=A)
+            eng.fe_square("fq", t2, out=x, flags=A)
+
+    eager = timed(eng, chain)
+    g = eng.graph_capture(chain)
+    graph = timed(eng, lambda: eng.graph_launch(g))
+    res["chain48_n4096"] = {"eager_ms": eager, "graph_ms": graph}
+    print(f"48-kernel chain at n=4096: eager {eager:.3f} ms, CUDA graph {graph:.3f} ms", flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_ops.json", "w"), indent=1)
 

@@ -427,3 +427,33 @@ def test_scalar_mul_differential_64k(eng, oracle):
     got = eng.scalar_mul(p, k, output="bytes")
     want = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(p, k)))
     assert (got == want).all()
+
+
+def test_cuda_graph_replay(eng, oracle):
+    """A captured chain of small field batches (x <- (x*y + y)^2, 16 times) replays bit-exactly."""
+    import jubjub_b200 as jj
+
+    n = 4096
+    x0, y0 = oracle.fe_stream(FQ, 31, n), oracle.fe_stream(FQ, 32, n)
+    x, y, t = eng.to_device(x0), eng.to_device(y0), eng.empty((n, 4))
+    A = jj.JJ_ASYNC
+
+    def chain():
+        for _ in range(16):
+            eng.fe_mul("fq", x, y, out=t, flags=A)
+            eng.fe_add("fq", t, y, out=t, flags=A)
+            eng.fe_square("fq", t, out=x, flags=A)
+
+    want = x0
+    for _ in range(16):
+        want = oracle.fe_batch(FQ, oracle.OP_SQUARE, oracle.fe_batch(FQ, oracle.OP_ADD, oracle.fe_batch(FQ, oracle.OP_MUL, want, y0), y0))
+    chain()
+    eng.sync()
+    assert (x.download() == want).all()
+    g = eng.graph_capture(chain)
+    for _ in range(3):
+        x.upload(x0)
+        eng.graph_launch(g)
+        eng.sync()
+        assert (x.download() == want).all()
+    eng.graph_destroy(g)
