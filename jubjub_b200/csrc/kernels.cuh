@@ -317,7 +317,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulAr
     extern __shared__ uint4 smem_tbl[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t stride = (size_t)gridDim.x * THREADS;
-    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < a.n; i += stride) {
+    // warp-major slot order: warp w of every block comes before warp w+1 of any block, so the last,
+    // partial round of the batch leaves every SM with the same number of busy warps instead of
+    // leaving whole SMs idle (the kernel is pipe-bound: fewer warps per SM finish proportionally sooner)
+    const size_t slot = ((size_t)warp * gridDim.x + blockIdx.x) * 32 + lane;
+    for (size_t i = slot; i < a.n; i += stride) {
         ext_point P, acc;
         fe k;
         ld_ext_stream(P, a.points, i);
