@@ -135,6 +135,56 @@ JJ_DEVICE void fe_cswap(fe& a, fe& b, bool c) {
     }
 }
 
+// ---- predicated modulus add / subtract / negate ----------------------------------------------
+// if (cond) d (+|-)= m, or d = m - d: eight predicated IADD3.X in one carry chain (the instructions issue
+// either way; what is saved is the 8 SEL / LOP3 of the select- or mask-based forms).
+#if defined(JJ_HOST_EMUL)
+template <class F>
+JJ_DEVICE void fe_cadd_mod(uint32_t d[8], uint32_t cond) {
+    if (!cond) return;
+    JJ_ADD_CC_I(d[0], d[0], F::M0); JJ_ADDC_CC_I(d[1], d[1], F::M1); JJ_ADDC_CC_I(d[2], d[2], F::M2);
+    JJ_ADDC_CC_I(d[3], d[3], F::M3); JJ_ADDC_CC_I(d[4], d[4], F::M4); JJ_ADDC_CC_I(d[5], d[5], F::M5);
+    JJ_ADDC_CC_I(d[6], d[6], F::M6); JJ_ADDC_I(d[7], d[7], F::M7);
+}
+template <class F>
+JJ_DEVICE void fe_csub_mod(uint32_t d[8], uint32_t cond) {
+    if (!cond) return;
+    JJ_SUB_CC_I(d[0], d[0], F::M0); JJ_SUBC_CC_I(d[1], d[1], F::M1); JJ_SUBC_CC_I(d[2], d[2], F::M2);
+    JJ_SUBC_CC_I(d[3], d[3], F::M3); JJ_SUBC_CC_I(d[4], d[4], F::M4); JJ_SUBC_CC_I(d[5], d[5], F::M5);
+    JJ_SUBC_CC_I(d[6], d[6], F::M6); JJ_SUBC_CC_I(d[7], d[7], F::M7);
+}
+template <class F>
+JJ_DEVICE void fe_cneg_mod(uint32_t d[8], uint32_t cond) {
+    if (!cond) return;
+    sub_cc(d[0], F::M0, d[0]); subc_cc(d[1], F::M1, d[1]); subc_cc(d[2], F::M2, d[2]); subc_cc(d[3], F::M3, d[3]);
+    subc_cc(d[4], F::M4, d[4]); subc_cc(d[5], F::M5, d[5]); subc_cc(d[6], F::M6, d[6]); subc(d[7], F::M7, d[7]);
+}
+#else
+#define JJ_PRED8(OP0, OPC, OPL, SWAP)                                                                             \
+    asm volatile(                                                                                                 \
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %8, 0;\n\t"                                                         \
+        "@p " OP0 " %0, " SWAP("%0", "%9") ";\n\t@p " OPC " %1, " SWAP("%1", "%10") ";\n\t"                         \
+        "@p " OPC " %2, " SWAP("%2", "%11") ";\n\t@p " OPC " %3, " SWAP("%3", "%12") ";\n\t"                        \
+        "@p " OPC " %4, " SWAP("%4", "%13") ";\n\t@p " OPC " %5, " SWAP("%5", "%14") ";\n\t"                        \
+        "@p " OPC " %6, " SWAP("%6", "%15") ";\n\t@p " OPL " %7, " SWAP("%7", "%16") ";\n\t}"                       \
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7])          \
+        : "r"(cond), "n"(F::M0), "n"(F::M1), "n"(F::M2), "n"(F::M3), "n"(F::M4), "n"(F::M5), "n"(F::M6), "n"(F::M7))
+#define JJ_ORD_DM(D, M) D ", " M
+#define JJ_ORD_MD(D, M) M ", " D
+template <class F>
+JJ_DEVICE void fe_cadd_mod(uint32_t d[8], uint32_t cond) {
+    JJ_PRED8("add.cc.u32", "addc.cc.u32", "addc.u32", JJ_ORD_DM);
+}
+template <class F>
+JJ_DEVICE void fe_csub_mod(uint32_t d[8], uint32_t cond) {
+    JJ_PRED8("sub.cc.u32", "subc.cc.u32", "subc.u32", JJ_ORD_DM);
+}
+template <class F>
+JJ_DEVICE void fe_cneg_mod(uint32_t d[8], uint32_t cond) {
+    JJ_PRED8("sub.cc.u32", "subc.cc.u32", "subc.u32", JJ_ORD_MD);
+}
+#endif
+
 // r in [0, 2m)  ->  [0, m): trial-subtract m, keep the difference unless it borrowed.
 // Same value as the reference's sub(&MODULUS) with mask add-back (src/fr.rs:587, 620-634).
 template <class F>
@@ -176,6 +226,9 @@ JJ_DEVICE void fe_sub(fe& r, const fe& a, const fe& b) {
 #pragma unroll
     for (int i = 1; i < 8; i++) subc_cc(d[i], a.w[i], b.w[i]);
     subc(mask, 0u, 0u);  // all-ones when a < b
+#if defined(JJ_PRED_SUB)
+    fe_cadd_mod<F>(d, mask);
+#else
     add_cc(d[0], d[0], F::M0 & mask);
     addc_cc(d[1], d[1], F::M1 & mask);
     addc_cc(d[2], d[2], F::M2 & mask);
@@ -184,6 +237,7 @@ JJ_DEVICE void fe_sub(fe& r, const fe& a, const fe& b) {
     addc_cc(d[5], d[5], F::M5 & mask);
     addc_cc(d[6], d[6], F::M6 & mask);
     addc(d[7], d[7], F::M7 & mask);
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) r.w[i] = d[i];
 }
@@ -229,7 +283,7 @@ JJ_DEVICE void redc_row(uint32_t E[8], uint32_t O[8]) {
     JJ_MADC_HI_CC_I(E[5], q, F::M4, E[5]);
     JJ_MADC_LO_CC_I(E[6], q, F::M6, E[6]);
     JJ_MADC_HI_CC_I(E[7], q, F::M6, E[7]);
-    addc(O[7], O[7], 0u);
+    addc(O[7], O[7], oz());
 }
 // Fq specialisation.  q's low limbs are m0 = 1, m1 = 2^32 - 1 and -q^-1 = 2^32 - 1, so
 //   k       = -E[0]                                   (no multiply)
@@ -241,11 +295,24 @@ JJ_DEVICE void redc_row(uint32_t E[8], uint32_t O[8]) {
 template <>
 JJ_DEVICE_SPEC void redc_row<FqP>(uint32_t E[8], uint32_t O[8]) {
     uint32_t e0 = E[0], q, hi, t;
-    sub_cc(q, 0u, e0);   // q = -e0, borrow = c0
+#if defined(JJ_REDC_M1_IMAD)
+    // (O[1]:O[0]) += k * m1 + c0 as ONE IMAD.WIDE.X whose carry-in is c0: 2 ALU + 1 multiplier
+    // instruction instead of 5 ALU instructions.  Measured faster: the ALU/issue side of this loop
+    // costs about as much as the multiplier side.
+    // (The borrow of the negation IS c0, but a madc/addc that consumes the flag of a sub.cc gets the
+    // un-inverted SASS predicate on sm_100a / CUDA 12.9 -- wrong results -- so c0 is regenerated.)
+    sub_cc(q, oz(), e0);         // q = -e0
+    add_cc(t, e0, 0xffffffffu);  // carry = c0 = [e0 != 0]
+    JJ_MADC_LO_CC_I(O[0], q, FqP::M1, O[0]);
+    JJ_MADC_HI_CC_I(O[1], q, FqP::M1, O[1]);
+    (void)hi;
+#else
+    sub_cc(q, oz(), e0);   // q = -e0, borrow = c0
     subc(hi, q, 0u);     // hi = q - c0
     add_cc(t, e0, 0xffffffffu);  // carry = c0
     addc_cc(O[0], O[0], e0);
     addc_cc(O[1], O[1], hi);
+#endif
     JJ_MADC_LO_CC_I(O[2], q, FqP::M3, O[2]);
     JJ_MADC_HI_CC_I(O[3], q, FqP::M3, O[3]);
     JJ_MADC_LO_CC_I(O[4], q, FqP::M5, O[4]);
@@ -258,7 +325,7 @@ JJ_DEVICE_SPEC void redc_row<FqP>(uint32_t E[8], uint32_t O[8]) {
     JJ_MADC_HI_CC_I(E[5], q, FqP::M4, E[5]);
     JJ_MADC_LO_CC_I(E[6], q, FqP::M6, E[6]);
     JJ_MADC_HI_CC_I(E[7], q, FqP::M6, E[7]);
-    addc(O[7], O[7], 0u);
+    addc(O[7], O[7], oz());
     E[0] = 0;
     (void)t;
 }
@@ -284,7 +351,7 @@ JJ_DEVICE void mul_row(uint32_t E[8], uint32_t O[8], const uint32_t a[8], uint32
     madc_hi_cc(E[5], a[4], bi, E[5]);
     madc_lo_cc(E[6], a[6], bi, E[6]);
     madc_hi_cc(E[7], a[6], bi, E[7]);
-    addc(O[7], O[7], 0u);
+    addc(O[7], O[7], oz());
 }
 // First row: nothing accumulated yet, plain 32x32->64 products (IMAD.WIDE.U32 with RZ).
 JJ_DEVICE void mul_row0(uint32_t E[8], uint32_t O[8], const uint32_t a[8], uint32_t b0) {
@@ -406,29 +473,33 @@ JJ_DEVICE void sqr_row(uint32_t E[8], uint32_t O[8], const uint32_t a[8], const 
             madc_lo_cc(E[6], sqr_operand<I, 6>(a, dw), bi, E[6]);
         }
         madc_hi_cc(E[7], sqr_operand<I, 6>(a, dw), bi, E[7]);
-        addc(O[7], O[7], 0u);
+        addc(O[7], O[7], oz());
     }
 }
 // x = a or m - a, whichever has its top limb <= m7 / 2 (then 2x + m < 2^256 (1 - 2^-32)).
 template <class F>
 JJ_DEVICE void sqr_fold(uint32_t x[8], const fe& a) {
-    if (3.0 * (double)F::M7 < 4294967295.0 * 0.999) {  // 3m < 2^256 already: nothing to do (Fr)
 #pragma unroll
-        for (int i = 0; i < 8; i++) x[i] = a.w[i];
-        return;
+    for (int i = 0; i < 8; i++) x[i] = a.w[i];
+    constexpr bool needed = !(3.0 * (double)F::M7 < 4294967295.0 * 0.999);  // 3m < 2^256 already (Fr): no fold
+    if (needed) {
+        const bool big = a.w[7] > (F::M7 >> 1);
+#if defined(JJ_PRED_FOLD)
+        fe_cneg_mod<F>(x, big ? 1u : 0u);
+#else
+        uint32_t n[8];
+        sub_cc(n[0], F::M0, a.w[0]);
+        subc_cc(n[1], F::M1, a.w[1]);
+        subc_cc(n[2], F::M2, a.w[2]);
+        subc_cc(n[3], F::M3, a.w[3]);
+        subc_cc(n[4], F::M4, a.w[4]);
+        subc_cc(n[5], F::M5, a.w[5]);
+        subc_cc(n[6], F::M6, a.w[6]);
+        subc(n[7], F::M7, a.w[7]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = big ? n[i] : a.w[i];
+#endif
     }
-    uint32_t n[8];
-    sub_cc(n[0], F::M0, a.w[0]);
-    subc_cc(n[1], F::M1, a.w[1]);
-    subc_cc(n[2], F::M2, a.w[2]);
-    subc_cc(n[3], F::M3, a.w[3]);
-    subc_cc(n[4], F::M4, a.w[4]);
-    subc_cc(n[5], F::M5, a.w[5]);
-    subc_cc(n[6], F::M6, a.w[6]);
-    subc(n[7], F::M7, a.w[7]);
-    const bool big = a.w[7] > (F::M7 >> 1);
-#pragma unroll
-    for (int i = 0; i < 8; i++) x[i] = big ? n[i] : a.w[i];
 }
 template <class F>
 JJ_DEVICE void mont_sqr(fe& r, const fe& a) {

@@ -16,6 +16,20 @@
 #pragma once
 #include <stdint.h>
 
+// Arithmetic formulation switches (all bit-identical results; JJ_BASELINE_ARITH restores the round-1
+// first-half formulation for A/B measurements):
+//   JJ_OPAQUE_ZERO   `x + carry` / `0 - x` take a never-written constant-bank zero as second source so
+//                    ptxas keeps them IADD3(.X) on the ALU pipe instead of IMAD.X / IMAD.MOV
+//   JJ_PRED_SUB      fe_sub adds the modulus back with 8 predicated IADD3.X (no mask AND)
+//   JJ_PRED_FOLD     the squaring's q - a fold is a predicated negate (no selects)
+//   JJ_REDC_M1_IMAD  Fq reduction row: k*m1 + c0 on the multiplier (1 IMAD.WIDE.X for 3 ALU instructions)
+#if !defined(JJ_BASELINE_ARITH)
+#define JJ_OPAQUE_ZERO 1
+#define JJ_PRED_SUB 1
+#define JJ_PRED_FOLD 1
+#define JJ_REDC_M1_IMAD 1
+#endif
+
 #if defined(JJ_HOST_EMUL)
 #define JJ_DEVICE static inline
 #define JJ_DEVICE_SPEC inline
@@ -34,6 +48,7 @@ JJ_DEVICE void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { uin
 JJ_DEVICE void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + g_cf; d = (uint32_t)t; g_cf = (uint32_t)(t >> 32); }
 JJ_DEVICE void madc_hi(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { d = (uint32_t)(((uint64_t)a * b) >> 32) + c + g_cf; }
 JJ_DEVICE uint32_t umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+JJ_DEVICE uint32_t oz() { return 0u; }
 }  // namespace jj
 // immediate-operand forms: on the host they are ordinary values
 #define JJ_MAD_LO_CC_I(d, a, IMM, c) jj::mad_lo_cc(d, a, (uint32_t)(IMM), c)
@@ -63,6 +78,16 @@ JJ_DEVICE void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm
 JJ_DEVICE void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
 JJ_DEVICE void madc_hi(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
 JJ_DEVICE uint32_t umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// "Opaque zero": a constant-bank word that is never written, so it reads as 0 but ptxas cannot
+// fold it.  `x + carry` written as addc(x, x, 0) is free to become IMAD.X (and 0 - x IMAD.MOV) on the
+// FMA-heavy pipe -- the pipe IMAD.WIDE saturates; with oz() as the addend the instruction has two
+// register/constant sources and stays an IADD3(.X) on the ALU pipe, without a false dependency.
+#if defined(JJ_OPAQUE_ZERO)
+__constant__ uint32_t g_opaque_zero;
+JJ_DEVICE uint32_t oz() { return g_opaque_zero; }
+#else
+JJ_DEVICE uint32_t oz() { return 0u; }
+#endif
 }  // namespace jj
 #define JJ_MAD_LO_CC_I(d, a, IMM, c) asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(IMM), "r"(c))
 #define JJ_MADC_LO_CC_I(d, a, IMM, c) asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(IMM), "r"(c))
