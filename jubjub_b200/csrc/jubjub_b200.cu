@@ -165,7 +165,11 @@ const SmulVariant kVariants[] = {
     {480, 1, TABLE_GMEM},      // 20: 15 warps/SM (<= 136 registers)
     {256, 2, TABLE_GMEM},      // 21: 16 warps/SM in two blocks (<= 128 registers)
     {576, 1, TABLE_GMEM},      // 22: 18 warps/SM (<= 113 registers, spills)
-    {640, 1, TABLE_GMEM},      // 23: 20 warps/SM (<= 102 registers, spills)
+    {640, 1, TABLE_GMEM},      // 23: 20 warps/SM (<= 96 registers: spill code only around the additions)
+    {768, 1, TABLE_GMEM},      // 24: 24 warps/SM (<= 80 registers)
+    {704, 1, TABLE_GMEM},      // 25: 22 warps/SM (<= 88 registers)
+    {896, 1, TABLE_GMEM},      // 26: 28 warps/SM (<= 72 registers)
+    {1024, 1, TABLE_GMEM},     // 27: 32 warps/SM (<= 64 registers)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
@@ -236,6 +240,10 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(21, 256, 2, TABLE_GMEM);
         V(22, 576, 1, TABLE_GMEM);
         V(23, 640, 1, TABLE_GMEM);
+        V(24, 768, 1, TABLE_GMEM);
+        V(25, 704, 1, TABLE_GMEM);
+        V(26, 896, 1, TABLE_GMEM);
+        V(27, 1024, 1, TABLE_GMEM);
         case 15: return launch_smul_slots<512, 1>(c, s, a, tbl, tbl_cap);
         case 16: return launch_smul_slots<384, 1>(c, s, a, tbl, tbl_cap);
         case 17: return launch_smul_slots<544, 1>(c, s, a, tbl, tbl_cap);

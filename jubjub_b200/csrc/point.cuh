@@ -147,15 +147,17 @@ JJ_DEVICE void into_extended_t(ext_point& r, const fe& cu, const fe& cv, const f
 template <bool INL>
 JJ_DEVICE void point_double_t(ext_point& r, const ext_point& p) {
     fe uu, vv, zz2, uv2, vpu, vmu, cu, ct;
+    // the reference's values (src/lib.rs:812-826), ordered so that u, v and the squares die as early as
+    // possible: fewer live registers across the four squarings
+    fe_add<FqP>(uv2, p.u, p.v);
     fqs<INL>(uu, p.u);
     fqs<INL>(vv, p.v);
-    fqs<INL>(zz2, p.z);
-    fe_dbl<FqP>(zz2, zz2);
-    fe_add<FqP>(uv2, p.u, p.v);
     fqs<INL>(uv2, uv2);
     fe_add<FqP>(vpu, vv, uu);
     fe_sub<FqP>(vmu, vv, uu);
     fe_sub<FqP>(cu, uv2, vpu);
+    fqs<INL>(zz2, p.z);
+    fe_dbl<FqP>(zz2, zz2);
     fe_sub<FqP>(ct, zz2, vmu);
     into_extended_t<INL>(r, cu, vpu, vmu, ct);
 }

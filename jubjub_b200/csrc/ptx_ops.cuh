@@ -27,7 +27,9 @@
 #define JJ_OPAQUE_ZERO 1
 #define JJ_PRED_SUB 1
 #define JJ_PRED_FOLD 1
+#if !defined(JJ_NO_REDC_M1_IMAD)
 #define JJ_REDC_M1_IMAD 1
+#endif
 #endif
 
 #if defined(JJ_HOST_EMUL)

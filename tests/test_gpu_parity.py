@@ -8,7 +8,7 @@ import pytest
 
 from oracle import model as M
 from tests.golden import reference_kats as K
-from tests.helpers import affine_raw, b32, fe, fe_int, scalar_bytes
+from tests.helpers import affine_raw, b32, edge_field_pairs, fe, fe_int, scalar_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -47,6 +47,25 @@ def test_field_ops_montgomery(eng, oracle, which, name):
     assert (eng.fe_square(name, a) == oracle.fe_batch(which, oracle.OP_SQUARE, a)).all()
     assert (eng.fe_neg(name, a) == oracle.fe_batch(which, oracle.OP_NEG, a)).all()
     assert (eng.fe_double(name, a) == oracle.fe_batch(which, oracle.OP_DOUBLE, a)).all()
+
+
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_field_ops_edge_pairs(eng, oracle, which, name):
+    """All ordered pairs of the adversarial values (fold boundary of the squaring, zero / all-ones limbs that
+    make the quotient digit 0 or carry out of every column, neighbours of 0, m/2 and m)."""
+    a, b = edge_field_pairs(M.Q if which == FQ else M.R_ORDER)
+    assert (eng.fe_mul(name, a, b) == oracle.fe_batch(which, oracle.OP_MUL, a, b)).all()
+    assert (eng.fe_add(name, a, b) == oracle.fe_batch(which, oracle.OP_ADD, a, b)).all()
+    assert (eng.fe_sub(name, a, b) == oracle.fe_batch(which, oracle.OP_SUB, a, b)).all()
+    assert (eng.fe_square(name, a) == oracle.fe_batch(which, oracle.OP_SQUARE, a)).all()
+    assert (eng.fe_neg(name, a) == oracle.fe_batch(which, oracle.OP_NEG, a)).all()
+    assert (eng.fe_double(name, a) == oracle.fe_batch(which, oracle.OP_DOUBLE, a)).all()
+    # values, not only agreement of two implementations: a sample against the big-integer model
+    m = M.Q if which == FQ else M.R_ORDER
+    rinv = pow(1 << 256, -1, m)
+    got = eng.fe_mul(name, a, b)
+    for i in range(0, len(a), 53):
+        assert M.from_limbs(got[i]) == M.from_limbs(a[i]) * M.from_limbs(b[i]) * rinv % m
 
 
 @pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
@@ -187,7 +206,7 @@ def _smul_case(oracle, n):
     return p, k
 
 
-@pytest.mark.parametrize("variant", list(range(0, 24)))
+@pytest.mark.parametrize("variant", list(range(0, 28)))
 def test_scalar_mul_variants(eng, oracle, variant):
     eng.set_scalar_mul_variant(variant)
     try:

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import model as M
-from tests.helpers import scalar_bytes
+from tests.helpers import edge_field_pairs, scalar_bytes
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FQ, FR = 0, 1
@@ -113,6 +113,9 @@ def test_emulated_field_arithmetic(emul, oracle, which):
     b = np.concatenate([edge[::-1], oracle.fe_stream(which, 2, 20000)])
     for op in range(6):
         assert (emul.fe(which, op, a, b) == oracle.fe_batch(which, op, a, b)).all(), op
+    ea, eb = edge_field_pairs(m)  # fold boundary, zero / all-ones limbs, neighbours of 0, m/2, m -- all pairs
+    for op in range(6):
+        assert (emul.fe(which, op, ea, eb) == oracle.fe_batch(which, op, ea, eb)).all(), ("edge", op)
     assert (emul.fe(which, 6, a[:200]) == oracle.fe_invert(which, a[:200])[0]).all()
     assert (emul.fe(which, 7, a) == oracle.fe_to_bytes(which, a).view(np.uint64)).all()
     raw = np.concatenate([a, np.full((3, 4), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)])
