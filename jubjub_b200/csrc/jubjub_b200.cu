@@ -840,7 +840,13 @@ int32_t jj_batch_from_bytes(jj_ctx* c, const void* in, void* out, uint8_t* ok, s
     Out outs[2] = {{out, 64}, {ok, 1}};
     bool zip216 = !(flags & JJ_PRE_ZIP216);
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
-        k_from_bytes<<<grid_for(c, cnt, 128, 8), 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], cnt, zip216);
+        // chains of ~8 encodings per thread: the Fermat inversion is amortised 8x while 4 x 128-thread blocks per
+        // SM stay resident; grid in whole multiples of the SM count
+        size_t blocks = (cnt + 128 * 8 - 1) / (128 * 8);
+        size_t per_wave = (size_t)c->sm_count * 4;
+        blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
+        blocks = std::min(blocks, (cnt + 127) / 128);
+        k_from_bytes<<<(int)blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], cnt, zip216);
         c->launches++;
         CU(c, cudaGetLastError());
         return JJ_OK;

@@ -231,11 +231,26 @@ JJ_DEVICE void point_to_niels(ext_niels& n, const ext_point& p) { point_to_niels
 JJ_DEVICE void affine_to_niels(aff_niels& n, const aff_point& p) { affine_to_niels_t<false>(n, p); }
 JJ_DEVICE void point_add(ext_point& r, const ext_point& p, const ext_point& q, bool sub) { point_add_t<false>(r, p, q, sub); }
 
+// Tail of AffinePoint::from_bytes_inner / batch_from_bytes (src/lib.rs:515-533, 603-622): u = sqrt(u2), sign fixed
+// from the parity of the canonical u, ZIP-216 rejection of the non-canonical encodings of (0, +-1).
+JJ_DEVICE bool point_decode_tail(aff_point& p, const fe& v, const fe& u2, uint32_t sign, bool zip216) {
+    fe u, un, uc;
+    fe_set_zero(p.u);
+    fe_set_zero(p.v);
+    if (!fq_sqrt(u, u2)) return false;
+    fe_to_canonical<FqP>(uc, u);
+    bool flip = ((uc.w[0] ^ sign) & 1u) != 0;
+    fe_neg<FqP>(un, u);
+    if (zip216 && fe_is_zero(u) && flip) return false;
+    fe_select(p.u, u, un, flip);
+    p.v = v;
+    return true;
+}
 // AffinePoint::from_bytes_inner (src/lib.rs:492-534) for one encoding held as 8 LE words.
 // Returns false (and leaves the zero point) for non-canonical v, off-curve v, or -- with zip216 --
 // the non-canonical encodings of (0, +-1) whose sign bit is set (ZIP 216, src/lib.rs:527-531).
 JJ_DEVICE bool point_from_bytes(aff_point& p, const fe& enc, bool zip216) {
-    fe vraw = enc, v, v2, num, den, inv, u2, u, un, uc, one, d;
+    fe vraw = enc, v, v2, num, den, inv, u2, one, d;
     uint32_t sign = vraw.w[7] >> 31;
     vraw.w[7] &= 0x7fffffffu;
     fe_set_zero(p.u);
@@ -250,18 +265,7 @@ JJ_DEVICE bool point_from_bytes(aff_point& p, const fe& enc, bool zip216) {
     fe_add<FqP>(den, one, den);         // 1 + d v^2 (never zero: -1/d is a non-residue)
     fe_invert<FqP>(inv, den);
     fq_mul(u2, num, inv);
-    if (!fq_sqrt(u, u2)) return false;
-    fe_to_canonical<FqP>(uc, u);
-    bool flip = ((uc.w[0] ^ sign) & 1u) != 0;
-    fe_neg<FqP>(un, u);
-    fe_select(p.u, u, un, flip);
-    p.v = v;
-    if (zip216 && fe_is_zero(u) && flip) {
-        fe_set_zero(p.u);
-        fe_set_zero(p.v);
-        return false;
-    }
-    return true;
+    return point_decode_tail(p, v, u2, sign, zip216);
 }
 JJ_DEVICE bool point_is_identity(const ext_point& p) {  // u == 0 and v == z  src/lib.rs:691-696
     return fe_is_zero(p.u) && fe_eq(p.v, p.z);

@@ -346,6 +346,25 @@ def test_batch_from_bytes(eng, oracle):
     assert okb.all() and (back == aff).all()
 
 
+def test_batch_from_bytes_long_chains(eng, oracle):
+    """More encodings than resident threads, so every thread runs Montgomery's trick over a chain of several
+    encodings (the reference's single batched inversion, src/lib.rs:596-600), with rejected encodings of every
+    kind (non-canonical v = skipped zero denominator, off-curve v, flipped sign) scattered through the chains."""
+    n = 2 * 75776 + 999
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 7, n))
+    enc = eng.affine_to_bytes(eng.batch_normalize(eng.scalar_mul_fixed(oracle.generator(), t)))
+    enc = enc.copy()
+    enc[5::11, 0] ^= 1          # v + 1 (or - 1): mostly off the curve
+    enc[3::97] = 0xFF           # non-canonical v
+    enc[50::101, 31] ^= 0x80    # other sign: still valid, u negated
+    enc[7::1013] = 0
+    enc[7::1013, 0] = 1         # (0, 1), the identity
+    got, ok = eng.batch_from_bytes(enc)
+    want, wok = oracle.batch_from_bytes(enc)
+    assert (ok == wok).all() and 0.8 * n < ok.sum() < n
+    assert (got[ok == 1] == want[wok == 1]).all() and (got[ok == 0] == 0).all()
+
+
 def test_find_eight_torsion_on_gpu(eng, oracle):
     """src/lib.rs:1680-1696: [r] G walks the 8-torsion subgroup."""
     g = oracle.affine_to_extended(affine_raw(oracle, [K.FULL_GENERATOR_RAW]))
