@@ -629,7 +629,8 @@ JJ_DEVICE bool fr_sqrt(fe& r, const fe& a) {
     r = s;
     return fe_eq(s2, a);
 }
-JJ_DEVICE bool fq_sqrt(fe& r, const fe& a) {
+// Tonelli-Shanks loop form (kept as the cross-check of the table-driven fq_sqrt below; same root).
+JJ_DEVICE bool fq_sqrt_ts(fe& r, const fe& a) {
     if (fe_is_zero(a)) {
         fe_set_zero(r);
         return true;
@@ -658,6 +659,117 @@ JJ_DEVICE bool fq_sqrt(fe& r, const fe& a) {
         mont_sqr<FqP>(z, t);
         mont_mul<FqP>(b, b, z);
         m = i;
+    }
+    r = x;
+    return true;
+}
+
+// ---- table-driven square root in Fq ------------------------------------------------------------------
+// q - 1 = 2^32 * T.  With x = a^((T+1)/2) and b = a^T (an element of the cyclic 2^32-torsion <g>, g = 7^T),
+// sqrt(a) = x * g^s where 2s = -log_g(b) (mod 2^32); a is a residue iff that logarithm is even.  The loop form
+// above finds s one set bit at a time (about 16 data-dependent rounds of up to 31 squarings, and a warp pays
+// the maximum over its lanes); here log_g(b) is read 8 bits at a time (Pohlig-Hellman): raising to 2^24,
+// 2^16, 2^8, 1 lands in the order-256 subgroup <g^(2^24)>, whose elements are recognised by a perfect hash of
+// 13 bits of their Montgomery limbs, and each recovered byte is divided out with one table product.
+// Fixed cost after the 222-bit power: 48 squarings + 9 products + 8 table reads, no data-dependent branches.
+// s is taken in [0, 2^31) like the loop form, so both return the same root.
+constexpr int kSqrtHashBits = 13, kSqrtHashLimb = 1, kSqrtHashShift = 11;
+struct alignas(32) FqSqrtTables {
+    fe neg[3][256];                    // g^(-i * 2^(8k)), k = 0, 1, 2
+    fe pos[4][256];                    // g^(+i * 2^(8k)), k = 0..3; pos[3] is the order-256 subgroup
+    uint8_t hash[1 << kSqrtHashBits];  // key(pos[3][i]) -> i
+    uint32_t ready;
+};
+#if defined(JJ_HOST_EMUL)
+static FqSqrtTables g_fq_sqrt_tab;
+#else
+__device__ FqSqrtTables g_fq_sqrt_tab;
+#endif
+JJ_DEVICE uint32_t fq_sqrt_key(const fe& y) {
+    return (y.w[kSqrtHashLimb] >> kSqrtHashShift) & ((1u << kSqrtHashBits) - 1u);
+}
+JJ_DEVICE void fe_load_tab(fe& r, const fe* p) {
+#if defined(JJ_HOST_EMUL)
+    r = *p;
+#else
+    const uint4* q4 = reinterpret_cast<const uint4*>(p);
+    uint4 lo = q4[0], hi = q4[1];
+    r.w[0] = lo.x; r.w[1] = lo.y; r.w[2] = lo.z; r.w[3] = lo.w;
+    r.w[4] = hi.x; r.w[5] = hi.y; r.w[6] = hi.z; r.w[7] = hi.w;
+#endif
+}
+// Fills the tables (one thread; ~1 900 products).  Returns false if the hash is not perfect on the subgroup
+// (it is, for the constants above: checked here at every initialisation and by the tests).
+JJ_DEVICE bool fq_sqrt_tables_build(FqSqrtTables& t) {
+    fe g, gi, one, sp, sn;
+#pragma unroll
+    for (int i = 0; i < 8; i++) g.w[i] = FqP::ROOT_OF_UNITY(i);
+    fe_invert<FqP>(gi, g);
+    fe_set_one<FqP>(one);
+    sp = g;
+    sn = gi;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        fe cp = one, cn = one;
+#pragma unroll 1
+        for (int i = 0; i < 256; i++) {
+            t.pos[k][i] = cp;
+            mont_mul<FqP>(cp, cp, sp);
+            if (k < 3) {
+                t.neg[k][i] = cn;
+                mont_mul<FqP>(cn, cn, sn);
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            mont_sqr<FqP>(sp, sp);
+            mont_sqr<FqP>(sn, sn);
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < (1 << kSqrtHashBits); i++) t.hash[i] = 0xff;
+    bool perfect = true;
+#pragma unroll 1
+    for (int i = 0; i < 256; i++) {
+        uint32_t key = fq_sqrt_key(t.pos[3][i]);
+        if (t.hash[key] != 0xff) perfect = false;
+        t.hash[key] = (uint8_t)i;
+    }
+    t.ready = perfect ? 1u : 0u;
+    return perfect;
+}
+JJ_DEVICE bool fq_sqrt(fe& r, const fe& a) {
+#if defined(JJ_HOST_EMUL)
+    if (!g_fq_sqrt_tab.ready) fq_sqrt_tables_build(g_fq_sqrt_tab);
+#endif
+    if (fe_is_zero(a)) {
+        fe_set_zero(r);
+        return true;
+    }
+    const FqSqrtTables& t = g_fq_sqrt_tab;
+    fe w, x, b, y, f;
+    fe_pow_const<FqP, ExpFqSqrt>(w, a);  // a^((T-1)/2)
+    mont_mul<FqP>(x, a, w);              // a^((T+1)/2)
+    mont_mul<FqP>(b, x, w);              // a^T
+    uint32_t dlog = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        y = b;
+#pragma unroll 1
+        for (int j = 0; j < 24 - 8 * k; j++) mont_sqr<FqP>(y, y);
+        uint32_t d = t.hash[fq_sqrt_key(y)];
+        dlog |= d << (8 * k);
+        if (k < 3) {
+            fe_load_tab(f, &t.neg[k][d & 255u]);
+            mont_mul<FqP>(b, b, f);  // divide the recovered byte out
+        }
+    }
+    if (dlog & 1u) return false;  // odd logarithm: a is a non-residue
+    uint32_t s = (0x80000000u - (dlog >> 1)) & 0x7fffffffu;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        fe_load_tab(f, &t.pos[k][(s >> (8 * k)) & 255u]);
+        mont_mul<FqP>(x, x, f);
     }
     r = x;
     return true;

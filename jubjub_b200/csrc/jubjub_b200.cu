@@ -489,6 +489,21 @@ int32_t jj_init(int device, jj_ctx** out) {
         jj_destroy(c);
         return JJ_ERR_CUDA;
     }
+    {   // device-resident tables of the table-driven Fq square root (decode path); idempotent per device
+        uint32_t* st = nullptr;
+        uint32_t host = 0;
+        ok = cudaMalloc(&st, sizeof(uint32_t)) == cudaSuccess;
+        if (ok) {
+            k_fq_sqrt_init<<<1, 32, 0, c->stream>>>(st);
+            ok = cudaMemcpyAsync(&host, st, sizeof(host), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                 cudaStreamSynchronize(c->stream) == cudaSuccess && host == 1u;
+            cudaFree(st);
+        }
+        if (!ok) {
+            jj_destroy(c);
+            return JJ_ERR_CUDA;
+        }
+    }
     *out = c;
     return JJ_OK;
 }

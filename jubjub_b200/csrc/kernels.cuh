@@ -582,6 +582,12 @@ __global__ void __launch_bounds__(128, 4) k_from_bytes(const char* __restrict__ 
     }
 }
 
+// Builds the Fq square-root tables (fe.cuh) once per device: one thread, ~1 900 products.  status[0] = 1 when the
+// subgroup hash came out perfect.
+__global__ void k_fq_sqrt_init(uint32_t* status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = fq_sqrt_tables_build(g_fq_sqrt_tab) ? 1u : 0u;
+}
+
 // Integer-multiplier peak probe: register-only, 8 independent accumulate chains per thread of
 // IMAD.WIDE.U32 (32x32+64 -> 64), the instruction the Montgomery kernels are made of and the
 // unit the scalar-mul roofline is counted in.  The multiplicand is the

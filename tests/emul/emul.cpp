@@ -125,6 +125,19 @@ extern "C" void emul_fq_sqrt(const void* a, void* out, uint8_t* ok, size_t n) {
     }
 }
 
+extern "C" void emul_fq_sqrt_ts(const void* a, void* out, uint8_t* ok, size_t n) {  // the loop form, for cross-checks
+    for (size_t i = 0; i < n; i++) {
+        fe r;
+        fe_set_zero(r);
+        ok[i] = fq_sqrt_ts(r, ((const fe*)a)[i]) ? 1 : 0;
+        ((fe*)out)[i] = r;
+    }
+}
+extern "C" int emul_fq_sqrt_tables_ok() {
+    static FqSqrtTables t;
+    return fq_sqrt_tables_build(t) ? 1 : 0;
+}
+
 extern "C" void emul_scalar_mul_slots(const void* p_, const void* k_, void* out_, size_t n) {
     for (size_t i = 0; i < n; i++) {
         uint32_t slots[S_COUNT * 8];

@@ -119,6 +119,25 @@ def test_field_sqrt(eng, oracle, which, name):
         assert int((ok == 0).sum()) == K.FR_SQRT_NONE_COUNT
 
 
+def test_fq_sqrt_torsion_ladder(eng, oracle):
+    """Fq::sqrt is table-driven on the device (logarithm in the 2^32-torsion, 8 bits at a time): inputs whose
+    a^T runs over the whole torsion ladder g^(c * 2^j), scaled copies, the edge values and their squares must give
+    the oracle's residue flags AND the oracle's root (Tonelli-Shanks, the same root choice)."""
+    from tests.helpers import edge_field_values
+
+    T = (M.Q - 1) >> 32
+    g = pow(7, T, M.Q)
+    tors = [pow(g, (c << j) % (1 << 32), M.Q) for j in range(32) for c in (1, 3, 0xFFFFFFFF, 0x9E3779B1, 0x80000001)]
+    tors += [x * 5 % M.Q for x in tors[:96]] + [x * x * 11 % M.Q for x in tors[:96]]
+    edge = edge_field_values(M.Q)
+    a = np.concatenate([np.array([M.limbs(M.to_mont(x, M.Q)) for x in tors], dtype=np.uint64), edge,
+                        oracle.fe_batch(FQ, oracle.OP_SQUARE, edge), oracle.fe_stream(FQ, M.SEED0 + 9, 20000)])
+    root, ok = eng.fe_sqrt("fq", a)
+    want, wok = oracle.fe_sqrt(FQ, a)
+    assert (ok == wok).all() and 0.3 * len(a) < ok.sum() < len(a)
+    assert (root[ok == 1] == want[wok == 1]).all() and (root[ok == 0] == 0).all()
+
+
 def test_fr_reference_kats_on_gpu(eng, oracle):
     """src/fr.rs:1045-1099 (LARGEST add/neg/sub), :1024-1034 (wide max), :1758-1776 (a*b==c)."""
     big, one_raw = fe(K.FR_LARGEST), fe([1, 0, 0, 0])

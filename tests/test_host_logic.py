@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import model as M
-from tests.helpers import edge_field_pairs, scalar_bytes
+from tests.helpers import edge_field_pairs, edge_field_values, scalar_bytes
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FQ, FR = 0, 1
@@ -174,12 +174,24 @@ def test_emulated_sqrt_and_decode(built, oracle):
 
     lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libjj_emul.so"))
     P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    a = oracle.fe_stream(FQ, 77, 300)
+    assert lib.emul_fq_sqrt_tables_ok() == 1  # the 13-bit hash is perfect on the order-256 subgroup
+    # random elements, 0, squares of the edge values, and the whole 2^32-torsion ladder g^(2^j), g^(3 * 2^j)
+    # (g = 7^T: the inputs whose a^T is not 1, i.e. the ones that exercise every byte of the logarithm)
+    edge = edge_field_values(M.Q)
+    T = (M.Q - 1) >> 32
+    g = pow(7, T, M.Q)
+    tors = [pow(g, (c << j) % (1 << 32), M.Q) for j in range(32) for c in (1, 3, 0xFFFFFFFF, 0x9E3779B1)]
+    tors += [x * 5 % M.Q for x in tors[:64]] + [x * x * 11 % M.Q for x in tors[:64]]
+    tors_m = np.array([M.limbs(M.to_mont(x, M.Q)) for x in tors], dtype=np.uint64)
+    a = np.concatenate([oracle.fe_stream(FQ, 77, 600), edge, oracle.fe_batch(FQ, oracle.OP_SQUARE, edge), tors_m])
     a[0] = 0
-    out, ok = np.zeros_like(a), np.zeros(len(a), np.uint8)
-    lib.emul_fq_sqrt(P(a), P(out), P(ok), C.c_size_t(len(a)))
-    assert (ok == oracle.fe_sqrt(FQ, a)[1]).all()
-    assert (oracle.fe_batch(FQ, oracle.OP_SQUARE, out[ok == 1]) == a[ok == 1]).all()
+    want, wok = oracle.fe_sqrt(FQ, a)
+    for fn in (lib.emul_fq_sqrt, lib.emul_fq_sqrt_ts):
+        out, ok = np.zeros_like(a), np.zeros(len(a), np.uint8)
+        fn(P(a), P(out), P(ok), C.c_size_t(len(a)))
+        assert (ok == wok).all() and 0.3 * len(a) < ok.sum() < len(a)
+        assert (oracle.fe_batch(FQ, oracle.OP_SQUARE, out[ok == 1]) == a[ok == 1]).all()
+        assert (out[ok == 1] == want[wok == 1]).all()  # the same root as the oracle's Tonelli-Shanks
     g = oracle.affine_to_extended(oracle.generator())
     t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 5, 120))
     enc = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(np.repeat(g, 120, axis=0), t)))
