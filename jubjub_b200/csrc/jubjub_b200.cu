@@ -349,6 +349,30 @@ int32_t fe_binary(jj_ctx* c, const void* a, const void* b, void* out, size_t n, 
         return fe_launch<F, OP>(c, s, canon, din[0], din[1], dout[0], nullptr, cnt, 0, 0);
     });
 }
+// Batched inversion: chains of ~32 elements per thread share one Fermat inversion (k_fe_invert_batched).
+template <class F>
+int32_t fe_invert_batch(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
+    In ins[3] = {{a, 32}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{out, 32}, {ok, 1}};
+    const bool canon = flags & JJ_CANON;
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
+        char** scr = S ? &S->tmp2 : &c->tmp2;
+        size_t* cap = S ? &S->tmp2_cap : &c->tmp2_cap;
+        int32_t rc = ensure(c, scr, cap, cnt * 32);
+        if (rc) return rc;
+        size_t blocks = (cnt + 128 * 32 - 1) / (128 * 32);
+        size_t per_wave = (size_t)c->sm_count * 2;
+        blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
+        blocks = std::min(blocks, (cnt + 127) / 128);
+        if (canon)
+            k_fe_invert_batched<F, true><<<(int)blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], *scr, cnt);
+        else
+            k_fe_invert_batched<F, false><<<(int)blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], *scr, cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
+    });
+}
 template <class F, int OP>
 int32_t fe_with_ok(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
     In ins[3] = {{a, 32}, {nullptr, 0}, {nullptr, 0}};
@@ -697,10 +721,10 @@ FE_UN(neg, FE_NEG)
 FE_UN(double, FE_DBL)
 
 int32_t jj_fq_invert(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
-    return fe_with_ok<FqP, FE_INV>(c, a, out, ok, n, flags);
+    return fe_invert_batch<FqP>(c, a, out, ok, n, flags);
 }
 int32_t jj_fr_invert(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
-    return fe_with_ok<FrP, FE_INV>(c, a, out, ok, n, flags);
+    return fe_invert_batch<FrP>(c, a, out, ok, n, flags);
 }
 int32_t jj_fq_sqrt(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
     return fe_with_ok<FqP, FE_SQRT>(c, a, out, ok, n, flags);

@@ -174,6 +174,45 @@ __global__ void __launch_bounds__(256) k_fe_op(const char* __restrict__ a, const
     }
 }
 
+// Batched inversion (the reference's Fr::invert / Fq::invert per element, src/fr.rs:438-540, CtOption::none
+// for 0 -> ok[i] = 0 and a zero result): Montgomery's trick along each thread's strided chain, exactly as
+// ff::BatchInverter does for batch_normalize (src/lib.rs:849, 1086), so a chain of ~32 elements costs ONE
+// Fermat inversion plus 3 products per element.  The inverse of a field element is unique, so the limbs
+// are the ones the reference's addition chain produces.  `scratch` (n x 32 B) holds the prefix products;
+// `out` may alias `a`.
+template <class F, bool CANON>
+__global__ void __launch_bounds__(128) k_fe_invert_batched(const char* __restrict__ a, char* out, uint8_t* __restrict__ ok,
+                                                           char* __restrict__ scratch, size_t n) {
+    const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    fe acc, x;
+    fe_set_one<F>(acc);
+    size_t cnt = 0;
+    for (size_t i = t; i < n; i += T, cnt++) {
+        ld_fe(x, a + i * 32);
+        if (CANON) fe_from_raw<F>(x, x);
+        st_fe(scratch + i * 32, acc);
+        if (!fe_is_zero(x)) mont_mul<F>(acc, acc, x);
+    }
+    fe_invert<F>(acc, acc);
+    for (size_t c = cnt; c-- > 0;) {
+        const size_t i = t + c * T;
+        fe pre, r;
+        ld_fe(x, a + i * 32);
+        if (CANON) fe_from_raw<F>(x, x);
+        ld_fe(pre, scratch + i * 32);
+        const bool nz = !fe_is_zero(x);
+        fe_set_zero(r);
+        if (nz) {
+            mont_mul<F>(r, pre, acc);
+            mont_mul<F>(acc, acc, x);
+        }
+        if (CANON) fe_to_canonical<F>(r, r);
+        st_fe(out + i * 32, r);
+        if (ok) ok[i] = nz ? 1 : 0;
+    }
+}
+
 // ---- point batches ---------------------------------------------------------------------------
 enum PtOp { PT_DBL = 0, PT_ADD, PT_ADD_NIELS, PT_ADD_AFFINE_NIELS, PT_TO_NIELS, PT_AFFINE_TO_NIELS };
 

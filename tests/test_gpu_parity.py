@@ -103,6 +103,32 @@ def test_field_invert_and_bytes(eng, oracle, which, name):
 
 
 @pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
+def test_field_invert_long_chains(eng, oracle, which, name):
+    """More elements than resident threads: every thread inverts a chain of several elements with Montgomery's
+    trick (zeros scattered through the chains are skipped and flagged, like ff::BatchInverter); also with
+    canonical-integer I/O and in place on the device."""
+    import jubjub_b200 as jj
+
+    n = 2 * 37888 + 517
+    a = oracle.fe_stream(which, M.SEED0 + 11, n)
+    a[::97] = 0
+    a[1::1013] = oracle.fe_one(which)[0]
+    inv, ok = eng.fe_invert(name, a)
+    winv, wok = oracle.fe_invert(which, a)
+    assert (ok == wok).all() and 700 < int((ok == 0).sum()) <= len(a[::97])
+    assert (inv == winv).all()
+    one = np.repeat(oracle.fe_one(which), n, axis=0)
+    assert (eng.fe_mul(name, a, inv)[ok == 1] == one[ok == 1]).all()
+    ca = oracle.fe_to_bytes(which, a).view(np.uint64)
+    cinv, cok = eng.fe_invert(name, ca, flags=jj.JJ_CANON)
+    assert (cok == wok).all() and (cinv == oracle.fe_to_bytes(which, winv).view(np.uint64)).all()
+    d = eng.to_device(a)
+    okd = eng.empty((n, 1), np.uint8)
+    eng._check(getattr(eng.lib, f"jj_{name}_invert")(eng.ctx, d.ptr, d.ptr, okd.ptr, n, jj.JJ_DEVICE_PTRS))  # out aliases a
+    assert (d.download() == winv).all() and (okd.download().ravel() == wok).all()
+
+
+@pytest.mark.parametrize("which,name", [(FQ, "fq"), (FR, "fr")])
 def test_field_sqrt(eng, oracle, which, name):
     """src/fr.rs:1205-1227 (47 non-residues among r-2, r-3, ...) and residue flags vs the oracle for both fields."""
     a, _ = _field_inputs(oracle, which, 2000)
