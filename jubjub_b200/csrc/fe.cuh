@@ -265,7 +265,7 @@ JJ_DEVICE void fe_neg(fe& r, const fe& a) {
 // After the row E[0] == 0.  The O chain cannot carry out (running total < 2^(32*9) at
 // this column, see DESIGN.md "carry bounds"); the E chain's carry lands in O[7].
 template <class F>
-JJ_DEVICE void redc_row(uint32_t E[8], uint32_t O[8]) {
+JJ_DEVICE void redc_row_generic(uint32_t E[8], uint32_t O[8]) {
     uint32_t q = E[0] * F::INV;
     JJ_MAD_LO_CC_I(O[0], q, F::M1, O[0]);
     JJ_MADC_HI_CC_I(O[1], q, F::M1, O[1]);
@@ -292,10 +292,13 @@ JJ_DEVICE void redc_row(uint32_t E[8], uint32_t O[8]) {
 // i.e. O[0] += E[0] + c0 and O[1] += k - c0, all IADD3 work on the ALU pipe.  That
 // removes 3 of the 17 integer-multiplier instructions of every row (136 -> 112 per
 // product) and leaves E[1] untouched.
-template <>
-JJ_DEVICE_SPEC void redc_row<FqP>(uint32_t E[8], uint32_t O[8]) {
+// M1MUL selects how k*m1 + c0 is added: true = one IMAD.WIDE.X (default of the point kernels, whose bound is the
+// issue rate), false = three IADD3 (the elementwise field kernels, which are HBM- or multiplier-bound and want
+// the fewest multiplier instructions).
+template <bool M1MUL>
+JJ_DEVICE void redc_row_fq(uint32_t E[8], uint32_t O[8]) {
     uint32_t e0 = E[0], q, hi, t;
-#if defined(JJ_REDC_M1_IMAD)
+    if (M1MUL) {
     // (O[1]:O[0]) += k * m1 + c0 as ONE IMAD.WIDE.X whose carry-in is c0: 2 ALU + 1 multiplier
     // instruction instead of 5 ALU instructions.  Measured faster: the ALU/issue side of this loop
     // costs about as much as the multiplier side.
@@ -305,14 +308,13 @@ JJ_DEVICE_SPEC void redc_row<FqP>(uint32_t E[8], uint32_t O[8]) {
     add_cc(t, e0, 0xffffffffu);  // carry = c0 = [e0 != 0]
     JJ_MADC_LO_CC_I(O[0], q, FqP::M1, O[0]);
     JJ_MADC_HI_CC_I(O[1], q, FqP::M1, O[1]);
-    (void)hi;
-#else
+    } else {
     sub_cc(q, oz(), e0);   // q = -e0, borrow = c0
     subc(hi, q, 0u);     // hi = q - c0
     add_cc(t, e0, 0xffffffffu);  // carry = c0
     addc_cc(O[0], O[0], e0);
     addc_cc(O[1], O[1], hi);
-#endif
+    }
     JJ_MADC_LO_CC_I(O[2], q, FqP::M3, O[2]);
     JJ_MADC_HI_CC_I(O[3], q, FqP::M3, O[3]);
     JJ_MADC_LO_CC_I(O[4], q, FqP::M5, O[4]);
@@ -328,6 +330,24 @@ JJ_DEVICE_SPEC void redc_row<FqP>(uint32_t E[8], uint32_t O[8]) {
     addc(O[7], O[7], oz());
     E[0] = 0;
     (void)t;
+    (void)hi;
+}
+#if defined(JJ_REDC_M1_IMAD)
+constexpr bool kM1MulDefault = true;
+#else
+constexpr bool kM1MulDefault = false;
+#endif
+template <class F, bool M1MUL>
+struct RedcRow {
+    static JJ_DEVICE_SPEC void run(uint32_t E[8], uint32_t O[8]) { redc_row_generic<F>(E, O); }
+};
+template <bool M1MUL>
+struct RedcRow<FqP, M1MUL> {
+    static JJ_DEVICE_SPEC void run(uint32_t E[8], uint32_t O[8]) { redc_row_fq<M1MUL>(E, O); }
+};
+template <class F, bool M1MUL = kM1MulDefault>
+JJ_DEVICE void redc_row(uint32_t E[8], uint32_t O[8]) {
+    RedcRow<F, M1MUL>::run(E, O);
 }
 // One product row for multiplier word bi.  On entry O is the array that was column-
 // aligned in the previous row: O[0] is dead (zeroed by redc_row), O[1] sits at this
@@ -378,25 +398,25 @@ JJ_DEVICE void mont_finish(fe& r, const uint32_t E[8], const uint32_t O[8]) {
 }
 
 // r = a * b * 2^-256 mod m.  `a` canonical, `b` any 256-bit value.  r may alias a or b.
-template <class F>
+template <class F, bool M1MUL = kM1MulDefault>
 JJ_DEVICE void mont_mul(fe& r, const fe& a, const fe& b) {
     uint32_t X[8], Y[8];
     mul_row0(X, Y, a.w, b.w[0]);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     mul_row(Y, X, a.w, b.w[1]);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     mul_row(X, Y, a.w, b.w[2]);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     mul_row(Y, X, a.w, b.w[3]);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     mul_row(X, Y, a.w, b.w[4]);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     mul_row(Y, X, a.w, b.w[5]);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     mul_row(X, Y, a.w, b.w[6]);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     mul_row(Y, X, a.w, b.w[7]);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     mont_finish<F>(r, Y, X);
 }
 
@@ -501,7 +521,7 @@ JJ_DEVICE void sqr_fold(uint32_t x[8], const fe& a) {
 #endif
     }
 }
-template <class F>
+template <class F, bool M1MUL = kM1MulDefault>
 JJ_DEVICE void mont_sqr(fe& r, const fe& a) {
     uint32_t X[8], Y[8], dw[8], x[8];
     sqr_fold<F>(x, a);
@@ -520,21 +540,21 @@ JJ_DEVICE void mont_sqr(fe& r, const fe& a) {
         e = (uint64_t)dw[6] * b0;                  X[6] = (uint32_t)e; X[7] = (uint32_t)(e >> 32);
         o = (uint64_t)dw[7] * b0;                  Y[6] = (uint32_t)o; Y[7] = (uint32_t)(o >> 32);
     }
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     sqr_row<1>(Y, X, x, dw);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     sqr_row<2>(X, Y, x, dw);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     sqr_row<3>(Y, X, x, dw);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     sqr_row<4>(X, Y, x, dw);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     sqr_row<5>(Y, X, x, dw);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     sqr_row<6>(X, Y, x, dw);
-    redc_row<F>(X, Y);
+    redc_row<F, M1MUL>(X, Y);
     sqr_row<7>(Y, X, x, dw);
-    redc_row<F>(Y, X);
+    redc_row<F, M1MUL>(Y, X);
     mont_finish<F>(r, Y, X);
 }
 

@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256) k_fe_op(const char* __restrict__ a, const
                 if (OP == FE_MUL || OP == FE_ADD || OP == FE_SUB) fe_from_raw<F>(y, y);
             }
             switch (OP) {
-                case FE_MUL: mont_mul<F>(r, x, y); break;
-                case FE_SQR: mont_sqr<F>(r, x); break;
+                case FE_MUL: mont_mul<F, false>(r, x, y); break;  // 112 multiplier instructions: stays HBM-bound (measured)
+                case FE_SQR: mont_sqr<F>(r, x); break;            // issue-bound at 64 B/op: the default form is faster
                 case FE_ADD: fe_add<F>(r, x, y); break;
                 case FE_SUB: fe_sub<F>(r, x, y); break;
                 case FE_NEG: fe_neg<F>(r, x); break;

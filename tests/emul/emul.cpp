@@ -24,6 +24,8 @@ static void fe_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
             case 6: fe_invert<F>(r, a[i]); break;
             case 7: fe_to_canonical<F>(r, a[i]); break;
             case 8: fe_from_raw<F>(r, a[i]); break;
+            case 10: mont_mul<F, false>(r, a[i], b[i]); break;  // k*m1 on the ALU pipe (elementwise kernels)
+            case 11: mont_sqr<F, false>(r, a[i]); break;
             default: fe_set_zero(r); r.w[0] = fe_is_canonical<F>(a[i]); break;
         }
         out[i] = r;

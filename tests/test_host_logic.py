@@ -116,6 +116,9 @@ def test_emulated_field_arithmetic(emul, oracle, which):
     ea, eb = edge_field_pairs(m)  # fold boundary, zero / all-ones limbs, neighbours of 0, m/2, m -- all pairs
     for op in range(6):
         assert (emul.fe(which, op, ea, eb) == oracle.fe_batch(which, op, ea, eb)).all(), ("edge", op)
+    for op, ref in ((10, 0), (11, 1)):  # the other reduction-row formulation (used by the elementwise kernels)
+        assert (emul.fe(which, op, a, b) == oracle.fe_batch(which, ref, a, b)).all(), op
+        assert (emul.fe(which, op, ea, eb) == oracle.fe_batch(which, ref, ea, eb)).all(), ("edge", op)
     assert (emul.fe(which, 6, a[:200]) == oracle.fe_invert(which, a[:200])[0]).all()
     assert (emul.fe(which, 7, a) == oracle.fe_to_bytes(which, a).view(np.uint64)).all()
     raw = np.concatenate([a, np.full((3, 4), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)])
