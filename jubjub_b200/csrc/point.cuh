@@ -115,9 +115,9 @@ JJ_DEVICE void point_neg(ext_point& r, const ext_point& p) {  // src/lib.rs:196-
 // Every formula exists in two instantiations: INL = true inlines the Fq product / square bodies
 // (best for kernels that use a formula once: the elementwise point kernels, the fixed-base loop, the
 // doubling of the variable-base loop), INL = false calls the shared noinline bodies (small code).
-template <bool INL>
+template <bool INL, bool M1 = kM1MulDefault>
 JJ_DEVICE void fqm(fe& r, const fe& a, const fe& b) {
-    if (INL) mont_mul<FqP>(r, a, b);
+    if (INL) mont_mul<FqP, M1>(r, a, b);
     else fq_mul(r, a, b);
 }
 template <bool INL>
@@ -132,12 +132,12 @@ constexpr bool kInlineDouble = false;
 #endif
 
 // completed point (u, v, z, t) -> extended (u*t, v*z, z*t, u, v)   (src/lib.rs:1052-1060)
-template <bool INL>
+template <bool INL, bool M1 = kM1MulDefault>
 JJ_DEVICE void into_extended_t(ext_point& r, const fe& cu, const fe& cv, const fe& cz, const fe& ct) {
     fe u, v, z;
-    fqm<INL>(u, cu, ct);
-    fqm<INL>(v, cv, cz);
-    fqm<INL>(z, cz, ct);
+    fqm<INL, M1>(u, cu, ct);
+    fqm<INL, M1>(v, cv, cz);
+    fqm<INL, M1>(z, cz, ct);
     r.t1 = cu;
     r.t2 = cv;
     r.u = u;
@@ -162,20 +162,20 @@ JJ_DEVICE void point_double_t(ext_point& r, const ext_point& p) {
     into_extended_t<INL>(r, cu, vpu, vmu, ct);
 }
 // p + n (sub = false) or p - n (sub = true); Z2 = nullptr means an affine-Niels operand (d = 2z).
-template <bool INL>
+template <bool INL, bool M1 = kM1MulDefault>
 JJ_DEVICE void point_add_core_t(ext_point& r, const ext_point& p, const fe& n_vpu, const fe& n_vmu, const fe* n_z,
                                 const fe& n_t2d, bool sub) {
     fe a, b, c, d, t, n1, n2;
     fe_select(n1, n_vmu, n_vpu, sub);  // multiplies (v - u)
     fe_select(n2, n_vpu, n_vmu, sub);  // multiplies (v + u)
     fe_sub<FqP>(t, p.v, p.u);
-    fqm<INL>(a, t, n1);
+    fqm<INL, M1>(a, t, n1);
     fe_add<FqP>(t, p.v, p.u);
-    fqm<INL>(b, t, n2);
-    fqm<INL>(c, p.t1, p.t2);
-    fqm<INL>(c, c, n_t2d);
+    fqm<INL, M1>(b, t, n2);
+    fqm<INL, M1>(c, p.t1, p.t2);
+    fqm<INL, M1>(c, c, n_t2d);
     if (n_z) {
-        fqm<INL>(d, p.z, *n_z);
+        fqm<INL, M1>(d, p.z, *n_z);
         fe_dbl<FqP>(d, d);
     } else {
         fe_dbl<FqP>(d, p.z);
@@ -187,15 +187,15 @@ JJ_DEVICE void point_add_core_t(ext_point& r, const ext_point& p, const fe& n_vp
     fe_sub<FqP>(dmc, d, c);
     fe_select(cz, dpc, dmc, sub);
     fe_select(ct, dmc, dpc, sub);
-    into_extended_t<INL>(r, cu, cv, cz, ct);
+    into_extended_t<INL, M1>(r, cu, cv, cz, ct);
 }
 template <bool INL>
 JJ_DEVICE void point_add_niels_t(ext_point& r, const ext_point& p, const ext_niels& n, bool sub) {
     point_add_core_t<INL>(r, p, n.vpu, n.vmu, &n.z, n.t2d, sub);
 }
-template <bool INL>
+template <bool INL, bool M1 = kM1MulDefault>
 JJ_DEVICE void point_add_aff_niels_t(ext_point& r, const ext_point& p, const aff_niels& n, bool sub) {
-    point_add_core_t<INL>(r, p, n.vpu, n.vmu, nullptr, n.t2d, sub);
+    point_add_core_t<INL, M1>(r, p, n.vpu, n.vmu, nullptr, n.t2d, sub);
 }
 template <bool INL>
 JJ_DEVICE void point_to_niels_t(ext_niels& n, const ext_point& p) {
