@@ -379,6 +379,25 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulAr
     }
 }
 
+// One scalar for the whole batch, given as its width-5 NAF (scalarmul.cuh): is_torsion_free with k = r
+// (src/lib.rs:709-711).  Same mapping and table scratch as k_scalar_mul; digits come from the kernel
+// parameters (uniform loads), so the add / no-add branch is warp-uniform.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_scalar_mul_const(const SmulArgs a, const NafDigits naf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    const size_t slot = ((size_t)warp * gridDim.x + blockIdx.x) * 32 + lane;
+    for (size_t i = slot; i < a.n; i += stride) {
+        ext_point P, acc;
+        ld_ext_stream(P, a.points, i);
+        size_t gwarp = (size_t)blockIdx.x * (THREADS / 32) + warp;
+        GmemTable t{a.tbl_scratch + gwarp * 32768 + lane * 32};
+        scalar_mul_wnaf_core(acc, P, naf, t);
+        if (a.flag_out) a.flag_out[i] = point_is_identity(acc) ? 1 : 0;
+        else smul_store(a, i, acc);
+    }
+}
+
 // Slot-file mapping (slotmul.cuh): the working set of each thread lives in 13 shared-memory slots
 // (13 KB per warp), field operations are shared noinline routines.  Window table in global scratch.
 template <int THREADS, int MIN_BLOCKS>

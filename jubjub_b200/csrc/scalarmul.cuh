@@ -97,6 +97,82 @@ JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_
     }
 }
 
+// ---- one scalar shared by the whole batch (is_torsion_free: the scalar is r) --------------------------
+// Every lane has the same digits, so a width-5 sliding-window NAF costs no divergence: digits are odd, in
+// [-15, 15], at most one in any 5 consecutive positions -- for r, 42 additions instead of the 58 non-zero
+// signed radix-16 digits.  The table holds the odd multiples 1P, 3P, ..., 15P (one doubling + 7 additions).
+struct NafDigits {
+    int8_t d[256];  // little-endian: k = sum d[i] 2^i
+    int top;        // index of the highest non-zero digit, -1 for k = 0
+};
+// Host side: width-5 NAF of the low 252 bits of a 256-bit little-endian scalar (the bits `multiply` consumes,
+// src/lib.rs:366-372).
+inline void wnaf5_recode(NafDigits& out, const uint32_t k_in[8]) {
+    uint32_t k[9];
+    for (int i = 0; i < 8; i++) k[i] = k_in[i];
+    k[7] &= 0x0fffffffu;
+    k[8] = 0;
+    out.top = -1;
+    for (int i = 0; i < 256; i++) {
+        int t = 0;
+        if (k[0] & 1u) {
+            t = (int)(k[0] & 31u);
+            if (t >= 16) t -= 32;
+            // k -= t
+            uint64_t carry = 0;
+            if (t > 0) {
+                uint64_t borrow = (uint64_t)t;
+                for (int w = 0; w < 9 && borrow; w++) {
+                    uint64_t v = (uint64_t)k[w];
+                    k[w] = (uint32_t)(v - borrow);
+                    borrow = v < borrow ? 1 : 0;
+                }
+            } else {
+                carry = (uint64_t)(-t);
+                for (int w = 0; w < 9 && carry; w++) {
+                    uint64_t v = (uint64_t)k[w] + carry;
+                    k[w] = (uint32_t)v;
+                    carry = v >> 32;
+                }
+            }
+            out.top = i;
+        }
+        out.d[i] = (int8_t)t;
+        for (int w = 0; w < 8; w++) k[w] = (k[w] >> 1) | (k[w + 1] << 31);
+        k[8] >>= 1;
+    }
+}
+// acc = [k] P for the batch-wide scalar whose NAF is `naf`.
+template <class Table>
+JJ_DEVICE void scalar_mul_wnaf_core(ext_point& acc, const ext_point& P, const NafDigits& naf, Table& tbl) {
+    {
+        ext_niels n2, nj;
+        ext_point cur, P2;
+        point_double(P2, P);
+        point_to_niels(n2, P2);
+        cur = P;
+        point_to_niels(nj, cur);
+        tbl.store(0, nj);
+#pragma unroll 1
+        for (int j = 1; j < 8; j++) {
+            point_add_niels(cur, cur, n2, false);
+            point_to_niels(nj, cur);
+            tbl.store(j, nj);
+        }
+    }
+    point_set_identity(acc);
+#pragma unroll 1
+    for (int i = naf.top; i >= 0; i--) {
+        point_double(acc, acc);
+        const int d = naf.d[i];
+        if (d != 0) {
+            ext_niels n;
+            tbl.load(((d < 0 ? -d : d) - 1) >> 1, n);
+            point_add_niels(acc, acc, n, d < 0);
+        }
+    }
+}
+
 // ---- fixed base -------------------------------------------------------------------------
 // Shared per-window table for one base B: entry (i, j) = affine-Niels of (j+1) * 2^(W*i) * B for
 // window i < NW = ceil(252 / W) and j < 2^(W-1), plus one entry 2^(W*NW) * B for the recoding's top

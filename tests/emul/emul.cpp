@@ -67,6 +67,20 @@ extern "C" void emul_scalar_mul(const void* p_, const void* k_, void* out_, size
         ((ext_point*)out_)[i] = acc;
     }
 }
+// one scalar k (32 LE bytes) for all points: the width-5 NAF path of is_torsion_free
+extern "C" int emul_scalar_mul_wnaf(const void* p_, const void* k_, void* out_, size_t n) {
+    NafDigits naf;
+    wnaf5_recode(naf, (const uint32_t*)k_);
+    for (size_t i = 0; i < n; i++) {
+        LocalTable tbl;
+        ext_point acc;
+        scalar_mul_wnaf_core(acc, ((const ext_point*)p_)[i], naf, tbl);
+        ((ext_point*)out_)[i] = acc;
+    }
+    int nz = 0;
+    for (int i = 0; i < 256; i++) nz += naf.d[i] != 0;
+    return nz;
+}
 // fixed-base table for window width W (4 or 7), same construction as k_fixed_table_build
 template <int W>
 static void fixed_table(const void* base_affine, uint32_t* table, int first, int count) {

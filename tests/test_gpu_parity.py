@@ -410,6 +410,21 @@ def test_batch_from_bytes_long_chains(eng, oracle):
     assert (got[ok == 1] == want[wok == 1]).all() and (got[ok == 0] == 0).all()
 
 
+def test_is_torsion_free_large_batch_property(eng, oracle):
+    """2^18 points P_i = [t_i] G with G of order 8r (src/lib.rs:1380-1396): P_i is torsion free exactly when
+    8 | t_i (src/lib.rs:709-711) -- a size-independent check of the shared-scalar (width-5 NAF of r) kernel --
+    and every [8] P_i is torsion free; a sample is also compared with the oracle's bitwise ladder."""
+    n = 1 << 18
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 13, n))
+    t[::5, 0] &= 0xF8  # make a fifth of the scalars multiples of 8
+    pts = eng.scalar_mul_fixed(oracle.generator(), t)
+    flags = eng.is_torsion_free(pts)
+    assert (flags == ((t[:, 0] & 7) == 0)).all() and 0.2 * n < flags.sum() < 0.4 * n
+    p8 = eng.point_double(eng.point_double(eng.point_double(pts)))
+    assert eng.is_torsion_free(p8).all()
+    assert (flags[:600] == oracle.is_torsion_free(pts[:600])).all()
+
+
 def test_find_eight_torsion_on_gpu(eng, oracle):
     """src/lib.rs:1680-1696: [r] G walks the 8-torsion subgroup."""
     g = oracle.affine_to_extended(affine_raw(oracle, [K.FULL_GENERATOR_RAW]))

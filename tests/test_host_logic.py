@@ -172,6 +172,31 @@ def test_emulated_points_and_scalar_mul(emul, oracle):
         assert (oracle.batch_normalize(emul.smul_fixed(tbl, k, w)) == want).all(), w
 
 
+def test_emulated_shared_scalar_wnaf(built, oracle):
+    """The width-5 NAF core behind is_torsion_free: [k]P for one k shared by the batch equals the oracle's ladder
+    (affine), for k = r (42 non-zero digits; [r]P = O exactly on the prime-order subgroup), r - 1, 0, 1, 2^251 + ..."""
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libjj_emul.so"))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    n = 12
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 91, n))
+    p = oracle.scalar_mul(np.repeat(g, n, axis=0), t)          # full-order points
+    p[n // 2:] = oracle.ext_mul_by_cofactor(p[n // 2:])         # ... and prime-order ones
+    r = M.R_ORDER
+    for k in (r, r - 1, 0, 1, 2, 31, 32, (1 << 251) + 0x5A5A5A5A5A5A5A5A, (1 << 252) - 1, (1 << 256) - 1):
+        kb = scalar_bytes(k)
+        out = np.zeros_like(p)
+        nz = lib.emul_scalar_mul_wnaf(P(p), P(kb), P(out), C.c_size_t(n))
+        want = oracle.scalar_mul(p, np.repeat(kb, n, axis=0))
+        assert (oracle.batch_normalize(out) == oracle.batch_normalize(want)).all(), hex(k)
+        if k == r:
+            assert nz == 42
+            aff = oracle.batch_normalize(out)
+            one = oracle.fe_one(FQ)[0]
+            assert (aff[n // 2:, :4] == 0).all() and (aff[n // 2:, 4:] == one).all()   # [r]P = (0, 1) on the subgroup
+            assert not (aff[:n // 2, :4] == 0).all()                                     # but not for full-order points
+
+
 def test_emulated_sqrt_and_decode(built, oracle):
     from tests.golden import reference_kats as K
 
