@@ -11,3 +11,9 @@ timeout 600 python scripts/bench_ops.py > gpurun_out/${tag}_bench_ops.txt 2>&1; 
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench_steps2.csv python bench.py --steps 2 --warmup 3 > /dev/null 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scalar_mul -s 1 -c 1 -o gpurun_out/${tag}_smul_prof python scripts/run_smul.py --logn 20 --reps 3 > /dev/null 2>&1; echo "ncu full rc=$?"
 cat gpurun_out/${tag}_bench_n1.json | cut -c1-600
+if [ -n "$SANITIZE" ]; then
+  for tool in memcheck racecheck; do
+    timeout 400 compute-sanitizer --tool $tool python scripts/sanitize.py > gpurun_out/${tag}_sanitizer_$tool.txt 2>&1; echo "$tool rc=$?"; tail -3 gpurun_out/${tag}_sanitizer_$tool.txt
+  done
+fi
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

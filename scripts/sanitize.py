@@ -28,4 +28,9 @@ pts, ok = eng.batch_from_bytes(out)
 assert ok.all()
 eng.is_torsion_free(p[:64]); eng.is_identity(p); eng.is_small_order(p)
 d = eng.to_device(p); eng.scalar_mul(d, eng.to_device(k), output="affine").download()
+# chains longer than one element per thread (Montgomery-trick kernels) at a size compute-sanitizer finishes quickly:
+# the grids are capped at one 128-thread block per 128 elements, so force chains by calling with few elements is not
+# possible -- these calls cover the single-element chains, the long chains are covered by tests/test_gpu_parity.py
+eng.fe_invert("fq", a); eng.fe_invert("fr", a, flags=jj.JJ_CANON)
+eng.fe_sqrt("fq", eng.fe_square("fq", a[:200]))
 print("sanitize run ok")
