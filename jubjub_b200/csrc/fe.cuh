@@ -397,6 +397,70 @@ JJ_DEVICE void mont_finish(fe& r, const uint32_t E[8], const uint32_t O[8]) {
     for (int i = 0; i < 8; i++) r.w[i] = s[i];
 }
 
+// Fq: the LAST reduction row subtracts E[0] * q instead of adding (2^32 - E[0]) * q (q = 1 mod 2^32, so the
+// quotient digit of the subtractive form is E[0] itself).  The result is the additive one minus q, i.e. it lies
+// in (-q, q) instead of [0, 2q): its sign is bit 255 of the 8-word value and the final correction becomes
+// "add q if negative" -- 1 + 8 predicated instructions instead of the 8 subtractions + 8 selects of
+// fe_reduce_once -- and the row itself needs no negation, no carry regeneration and no k * m1 product.
+// Subtracting is adding E[0] * (2^288 - q) modulo the 9-word window: 2^288 - q has limbs
+// (2^32 - 1, 0, ~m2, ..., ~m7, 2^32 - 1); column 0 cancels into a plain E[0] at column 1, column 8 receives
+// -E[0] and everything above the window is dropped, as any carry out of it always was.
+#if defined(JJ_LAST_ROW_SUB)
+constexpr bool kLastRowSub = true;
+#else
+constexpr bool kLastRowSub = false;
+#endif
+JJ_DEVICE void redc_row_fq_last(uint32_t E[8], uint32_t O[8]) {
+    const uint32_t e0 = E[0];
+    add_cc(O[0], O[0], e0);
+    addc_cc(O[1], O[1], oz());
+    JJ_MADC_LO_CC_I(O[2], e0, (uint32_t)~FqP::M3, O[2]);
+    JJ_MADC_HI_CC_I(O[3], e0, (uint32_t)~FqP::M3, O[3]);
+    JJ_MADC_LO_CC_I(O[4], e0, (uint32_t)~FqP::M5, O[4]);
+    JJ_MADC_HI_CC_I(O[5], e0, (uint32_t)~FqP::M5, O[5]);
+    JJ_MADC_LO_CC_I(O[6], e0, (uint32_t)~FqP::M7, O[6]);
+    JJ_MADC_HI_I(O[7], e0, (uint32_t)~FqP::M7, O[7]);
+    JJ_MAD_LO_CC_I(E[2], e0, (uint32_t)~FqP::M2, E[2]);
+    JJ_MADC_HI_CC_I(E[3], e0, (uint32_t)~FqP::M2, E[3]);
+    JJ_MADC_LO_CC_I(E[4], e0, (uint32_t)~FqP::M4, E[4]);
+    JJ_MADC_HI_CC_I(E[5], e0, (uint32_t)~FqP::M4, E[5]);
+    JJ_MADC_LO_CC_I(E[6], e0, (uint32_t)~FqP::M6, E[6]);
+    JJ_MADC_HI_CC_I(E[7], e0, (uint32_t)~FqP::M6, E[7]);
+    addc(O[7], O[7], oz());
+    O[7] -= e0;
+    E[0] = 0;
+}
+// merge + "add q if negative" (pairs with redc_row_fq_last)
+JJ_DEVICE void mont_finish_signed_fq(fe& r, const uint32_t E[8], const uint32_t O[8]) {
+    uint32_t s[8];
+    add_cc(s[0], O[0], E[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(s[i], O[i], E[i + 1]);
+    addc(s[7], O[7], 0u);
+    fe_cadd_mod<FqP>(s, s[7] >> 31);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = s[i];
+}
+template <class F, bool M1MUL>
+struct LastRow {
+    static JJ_DEVICE_SPEC void run(fe& r, uint32_t E[8], uint32_t O[8]) {
+        redc_row<F, M1MUL>(E, O);
+        mont_finish<F>(r, E, O);
+    }
+};
+template <bool M1MUL>
+struct LastRow<FqP, M1MUL> {
+    static JJ_DEVICE_SPEC void run(fe& r, uint32_t E[8], uint32_t O[8]) {
+        if (kLastRowSub) {
+            redc_row_fq_last(E, O);
+            mont_finish_signed_fq(r, E, O);
+        } else {
+            redc_row<FqP, M1MUL>(E, O);
+            mont_finish<FqP>(r, E, O);
+        }
+    }
+};
+
 // r = a * b * 2^-256 mod m.  `a` canonical, `b` any 256-bit value.  r may alias a or b.
 template <class F, bool M1MUL = kM1MulDefault>
 JJ_DEVICE void mont_mul(fe& r, const fe& a, const fe& b) {
@@ -416,8 +480,7 @@ JJ_DEVICE void mont_mul(fe& r, const fe& a, const fe& b) {
     mul_row(X, Y, a.w, b.w[6]);
     redc_row<F, M1MUL>(X, Y);
     mul_row(Y, X, a.w, b.w[7]);
-    redc_row<F, M1MUL>(Y, X);
-    mont_finish<F>(r, Y, X);
+    LastRow<F, M1MUL>::run(r, Y, X);
 }
 
 // ---- Montgomery squaring ---------------------------------------------------------------
@@ -554,8 +617,7 @@ JJ_DEVICE void mont_sqr(fe& r, const fe& a) {
     sqr_row<6>(X, Y, x, dw);
     redc_row<F, M1MUL>(X, Y);
     sqr_row<7>(Y, X, x, dw);
-    redc_row<F, M1MUL>(Y, X);
-    mont_finish<F>(r, Y, X);
+    LastRow<F, M1MUL>::run(r, Y, X);
 }
 
 // Montgomery form -> canonical integer: one reduction of (a, 0), i.e. a * 1 (src/fr.rs:296-308).

@@ -264,8 +264,10 @@ struct Out {
     size_t unit;
 };
 // Launch(stream, din[3], dout[2], count, staging_or_null) -> status
+// chunk_units (<= kChunkUnits): units per staged chunk of a host-pointer call.
 template <class Launch>
-int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const Out (&outs)[2], Launch launch) {
+int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const Out (&outs)[2], Launch launch,
+                  size_t chunk_units = kChunkUnits) {
     if (!c) return JJ_ERR_INVALID_ARG;
     for (const In& i : ins)
         if (i.unit && !i.p && n) return fail(c, JJ_ERR_INVALID_ARG, "null input pointer");
@@ -290,7 +292,7 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
     size_t done = 0;
     int stage = 0;
     while (done < n) {
-        size_t cnt = std::min(kChunkUnits, n - done);
+        size_t cnt = std::min(chunk_units, n - done);
         Staging& S = c->st[stage];
         const char* din[3] = {nullptr, nullptr, nullptr};
         char* dout[2] = {nullptr, nullptr};
@@ -821,6 +823,14 @@ int32_t jj_scalar_mul(jj_ctx* c, const void* points, const void* scalars, void* 
     In ins[3] = {{points, 160}, {scalars, 32}, {nullptr, 0}};
     Out outs[2] = {{out, out_unit(flags)}, {nullptr, 0}};
     bool smont = flags & JJ_SCALAR_MONT, conv = flags & (JJ_OUT_AFFINE | JJ_OUT_BYTES);
+    // host batches are staged in chunks of whole "rounds" (one unit per resident thread): a chunk that ends in a
+    // partly filled round leaves the multiplier pipe under-occupied for that round
+    size_t chunk = kChunkUnits;
+    {
+        int v = c->smul_variant > 0 && c->smul_variant < kNumVariants ? c->smul_variant : kDefaultVariant;
+        size_t round = (size_t)c->sm_count * kVariants[v].threads * kVariants[v].min_blocks;
+        if (round && round <= kChunkUnits) chunk = kChunkUnits / round * round;
+    }
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
         char** tbl = S ? &S->tbl : &c->tbl;
         size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
@@ -833,7 +843,7 @@ int32_t jj_scalar_mul(jj_ctx* c, const void* points, const void* scalars, void* 
         rc = launch_smul(c, s, din[0], din[1], 32, *tmp, nullptr, cnt, tbl, tcap, smont);
         if (rc) return rc;
         return finish_output(c, s, *tmp, dout[0], cnt, flags, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap);
-    });
+    }, chunk);
 }
 
 int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scalars, void* out, size_t n, uint32_t flags) {

@@ -23,12 +23,17 @@
 //   JJ_PRED_SUB      fe_sub adds the modulus back with 8 predicated IADD3.X (no mask AND)
 //   JJ_PRED_FOLD     the squaring's q - a fold is a predicated negate (no selects)
 //   JJ_REDC_M1_IMAD  Fq reduction row: k*m1 + c0 on the multiplier (1 IMAD.WIDE.X for 3 ALU instructions)
+//   JJ_LAST_ROW_SUB  Fq: the last reduction row subtracts E[0]*q, the result is in (-q, q) and is fixed by a
+//                    sign-predicated add (fe.cuh, redc_row_fq_last)
 #if !defined(JJ_BASELINE_ARITH)
 #define JJ_OPAQUE_ZERO 1
 #define JJ_PRED_SUB 1
 #define JJ_PRED_FOLD 1
 #if !defined(JJ_NO_REDC_M1_IMAD)
 #define JJ_REDC_M1_IMAD 1
+#endif
+#if !defined(JJ_NO_LAST_ROW_SUB)
+#define JJ_LAST_ROW_SUB 1
 #endif
 #endif
 
