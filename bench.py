@@ -39,12 +39,12 @@ WORKLOAD = "2^20 variable-base ExtendedPoint*Fr scalar-muls per GPU (P_i=[t_i]G,
 # algorithmic work per unit (DESIGN.md "roofline"): bytes = 160 B point + 32 B scalar in, 160 B point out;
 # IMAD.WIDE.U32 = signed radix-16 window: 252 doublings (4S+3M), 7+~59 additions (8M), 16 M for to_niels,
 # S = 84 and M = 112 multiplier instructions: the minimum of 8x32-bit Montgomery with q's special low limbs.  (The
-# shipped kernels issue S = 92, M = 120 -- one extra multiply per reduction row replaces three ALU instructions,
+# shipped kernels issue S = 91, M = 119 -- one extra multiply per reduction row but the last replaces three ALU instructions,
 # DESIGN.md section 5 -- so the fraction below undercounts the pipe's real occupancy: ncu reads 86 %.)
 BYTES_PER_UNIT = 352
 # DRAM bytes of one 2^20-unit launch of the dominant kernel, from the committed ncu capture
-# profiles/r01c_ncu_scalar_mul_default_n1048576.csv (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_DRAM_BYTES_PER_LAUNCH = 238.15e6 + 752.25e6
+# profiles/r01d_ncu_scalar_mul_default_n1048576.csv (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_DRAM_BYTES_PER_LAUNCH = 235.93e6 + 752.27e6
 IMADS_PER_UNIT = 252 * (4 * 84 + 3 * 112) + (7 + 63 * 15 / 16) * 8 * 112 + 16 * 112
 GEN_RAW = np.array([[0xE4B3D35DF1A7ADFE, 0xCAF55D1B29BF81AF, 0x8B0F03DDD60A8187, 0x62EDCBB8BF3787C8, 0xB, 0, 0, 0]],
                    dtype=np.uint64)
@@ -338,7 +338,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_note": "bytes per launch, ncu capture profiles/r01c_ncu_scalar_mul_default_n1048576.csv; "
+                     "traffic_note": "bytes per launch, ncu capture profiles/r01d_ncu_scalar_mul_default_n1048576.csv; "
                                      "algorithmic bytes per launch = 352 B x 2^20 = 3.69e8; the excess is write-back of the L2 window-table "
                                      "scratch (0.4 % of HBM bandwidth, not re-reads of inputs)",
                      "peak_source": peak_src,
