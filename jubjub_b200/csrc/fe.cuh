@@ -289,9 +289,10 @@ JJ_DEVICE void redc_row_generic(uint32_t E[8], uint32_t O[8]) {
 //   k       = -E[0]                                   (no multiply)
 //   k * m0  : column 0 cancels E[0]; its carry c0 = [E[0] != 0] moves one column up
 //   k * m1  = k * 2^32 - k : low word = E[0], high word = k - c0
-// i.e. O[0] += E[0] + c0 and O[1] += k - c0, all IADD3 work on the ALU pipe.  That
-// removes 3 of the 17 integer-multiplier instructions of every row (136 -> 112 per
-// product) and leaves E[1] untouched.
+// i.e. O[0] += E[0] + c0 and O[1] += k - c0.  Done with IADD3s that is 14 multiplier instructions per
+// row instead of the generic 17 (112 per product); done as ONE IMAD.WIDE.X with carry-in c0 it is 15 per
+// row (119 per product with the subtractive last row below) and three ALU instructions fewer.  E[1] is
+// untouched either way.
 // M1MUL selects how k*m1 + c0 is added: true = one IMAD.WIDE.X (default of the point kernels, whose bound is the
 // issue rate), false = three IADD3 (the elementwise field kernels, which are HBM- or multiplier-bound and want
 // the fewest multiplier instructions).
@@ -486,7 +487,7 @@ JJ_DEVICE void mont_mul(fe& r, const fe& a, const fe& b) {
 // ---- Montgomery squaring ---------------------------------------------------------------
 // a^2 = sum_i a_i B^i (a_i B^i + 2 * sum_{j>i} a_j B^j): row i multiplies a_i by the vector
 // (a_i, 2a_{i+1}, ..., 2a_7) taken from the bit-doubled operand, so only 8 - i products are
-// issued (36 IMAD.WIDE instead of 64; total 36 + 48 = 84 for Fq).  Columns below the first
+// issued (36 IMAD.WIDE instead of 64; with Fq's reduction rows 84 .. 91 in total).  Columns below the first
 // product of a chain only propagate the merge carry (addc).
 //
 // Row i already contains the doubled cross terms of later rows, so the running total is bounded

@@ -92,7 +92,6 @@ struct jj_ctx {
     char fixed_base_key[64];
     bool fixed_valid = false;
     int fixed_w = 0;
-    char* const_scalar = nullptr;  // r, for is_torsion_free
     char* flush = nullptr;
     size_t flush_bytes = 0;
     void* nccl_comm = nullptr;
@@ -555,7 +554,7 @@ int32_t jj_destroy(jj_ctx* c) {
         if (c->st[k].stream) cudaStreamDestroy(c->st[k].stream);
     }
     for (void* p : {(void*)c->tbl, (void*)c->tmp, (void*)c->tmp2, (void*)c->fixed_table, (void*)c->fixed_base_dev,
-                    (void*)c->const_scalar, (void*)c->flush})
+                    (void*)c->flush})
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

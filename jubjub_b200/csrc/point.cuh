@@ -45,7 +45,7 @@ struct Curve {
 
 // Fq product / square as used by the point formulas.  On the device they are real (noinline)
 // functions: arguments and result travel in registers (no stack frame), and every point formula
-// shares ONE copy of the 112- / 84-multiplier bodies.  Fully inlined, the scalar-mul loop body is
+// shares ONE copy of the product and squaring bodies (119 / 91 multiplier instructions).  Fully inlined, the scalar-mul loop body is
 // 53 KB of straight-line code, which misses the instruction cache as soon as more than 8 warps per
 // SM run it (ncu: stall_no_instruction 1.7 per issue at 16 warps); with shared bodies the loop is
 // ~15 KB and 12-16 warps/SM keep the multiplier pipe busy.
