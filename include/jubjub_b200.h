@@ -161,6 +161,14 @@ int32_t jj_affine_to_niels(jj_ctx* ctx, const void* p_affine, void* out_aniels, 
  * Output: ExtendedPoint (projectively equal to the reference's, affine-identical), or with
  * JJ_OUT_AFFINE / JJ_OUT_BYTES the normalised point / its encoding (bit-exact). */
 int32_t jj_scalar_mul(jj_ctx* ctx, const void* points_ext, const void* scalars32, void* out, size_t n, uint32_t flags);
+/* Wire format in: points32[i] is the 32-byte encoding of an AffinePoint (src/lib.rs:455-464).  Decodes on the
+ * device exactly as jj_batch_from_bytes (ZIP-216 rule unless JJ_PRE_ZIP216), multiplies by scalars32[i] and writes
+ * the result in the format of jj_scalar_mul (Extended, JJ_OUT_AFFINE or JJ_OUT_BYTES).  ok[i] = 0 marks a rejected
+ * encoding; its output unit is then unspecified.  This is `AffinePoint::from_bytes(..) * scalar` for a whole batch
+ * with nothing but public types of the reference crate on the caller's side. */
+int32_t jj_scalar_mul_encoded(jj_ctx* ctx, const void* points32, const void* scalars32, void* out, uint8_t* ok, size_t n,
+                              uint32_t flags);
+
 /* out[i] = [scalars[i]] base: `&AffinePoint * &Fr` src/lib.rs:1109-1115 -> AffineNielsPoint::multiply :271-295,
  * one shared base; the per-window AffineNiels table is built once per base and cached in ctx. */
 int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* scalars32, void* out, size_t n, uint32_t flags);

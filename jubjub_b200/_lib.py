@@ -53,6 +53,7 @@ PROTOTYPES = {
     "jj_point_double": _UNARY, "jj_point_add": _BINARY, "jj_point_add_niels": _BINARY,
     "jj_point_add_affine_niels": _BINARY, "jj_point_to_niels": _UNARY, "jj_affine_to_niels": _UNARY,
     "jj_scalar_mul": _BINARY, "jj_scalar_mul_fixed": _BINARY,
+    "jj_scalar_mul_encoded": [_vp, _vp, _vp, _vp, _sz, _u32],
     "jj_batch_normalize": _UNARY, "jj_affine_to_bytes": _UNARY,
     "jj_batch_from_bytes": _WITH_OK,
     "jj_is_torsion_free": _UNARY, "jj_is_identity": _UNARY, "jj_is_small_order": _UNARY,

@@ -417,6 +417,18 @@ int32_t normalize_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, s
     CU(c, cudaGetLastError());
     return JJ_OK;
 }
+int32_t from_bytes_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, uint8_t* ok, size_t n, bool zip216) {
+    // chains of ~8 encodings per thread: the Fermat inversion is amortised 8x while 4 x 128-thread blocks per
+    // SM stay resident; grid in whole multiples of the SM count
+    size_t blocks = (n + 128 * 8 - 1) / (128 * 8);
+    size_t per_wave = (size_t)c->sm_count * 4;
+    blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
+    blocks = std::min(blocks, (n + 127) / 128);
+    k_from_bytes<<<(int)blocks, 128, 0, s>>>(in, out, ok, n, zip216);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return JJ_OK;
+}
 int32_t to_bytes_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, size_t n) {
     k_affine_to_bytes<<<grid_for(c, n, 256, 8), 256, 0, s>>>(in, out, n);
     c->launches++;
@@ -845,6 +857,37 @@ int32_t jj_scalar_mul(jj_ctx* c, const void* points, const void* scalars, void* 
     }, chunk);
 }
 
+int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scalars, void* out, uint8_t* ok, size_t n,
+                              uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    In ins[3] = {{points32, 32}, {scalars, 32}, {nullptr, 0}};
+    Out outs[2] = {{out, out_unit(flags)}, {ok, 1}};
+    const bool smont = flags & JJ_SCALAR_MONT, conv = flags & (JJ_OUT_AFFINE | JJ_OUT_BYTES), zip216 = !(flags & JJ_PRE_ZIP216);
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
+        // decode -> affine scratch -> extended scratch -> scalar-mul (in place when the output is converted)
+        char** tbl = S ? &S->tbl : &c->tbl;
+        size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
+        char** ext = S ? &S->buf[2] : &c->tmp;
+        size_t* extcap = S ? &S->cap[2] : &c->tmp_cap;
+        char** aff = S ? &S->tmp2 : &c->tmp2;
+        size_t* affcap = S ? &S->tmp2_cap : &c->tmp2_cap;
+        const size_t cap_units = std::max(cnt, S ? kChunkUnits : cnt);
+        int32_t rc = ensure(c, ext, extcap, cap_units * 160);
+        if (rc) return rc;
+        rc = ensure(c, aff, affcap, cap_units * 64);
+        if (rc) return rc;
+        rc = from_bytes_launch(c, s, din[0], *aff, (uint8_t*)dout[1], cnt, zip216);
+        if (rc) return rc;
+        k_affine_to_extended<<<grid_for(c, cnt, 256, 8), 256, 0, s>>>(*aff, *ext, cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        rc = launch_smul(c, s, *ext, din[1], 32, conv ? *ext : dout[0], nullptr, cnt, tbl, tcap, smont);
+        if (rc || !conv) return rc;
+        return finish_output(c, s, *ext, dout[0], cnt, flags, aff, affcap);
+    });
+}
+
 int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scalars, void* out, size_t n, uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;
     if (!base_affine) return fail(c, JJ_ERR_INVALID_ARG, "null base point");
@@ -895,16 +938,7 @@ int32_t jj_batch_from_bytes(jj_ctx* c, const void* in, void* out, uint8_t* ok, s
     Out outs[2] = {{out, 64}, {ok, 1}};
     bool zip216 = !(flags & JJ_PRE_ZIP216);
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
-        // chains of ~8 encodings per thread: the Fermat inversion is amortised 8x while 4 x 128-thread blocks per
-        // SM stay resident; grid in whole multiples of the SM count
-        size_t blocks = (cnt + 128 * 8 - 1) / (128 * 8);
-        size_t per_wave = (size_t)c->sm_count * 4;
-        blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
-        blocks = std::min(blocks, (cnt + 127) / 128);
-        k_from_bytes<<<(int)blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], cnt, zip216);
-        c->launches++;
-        CU(c, cudaGetLastError());
-        return JJ_OK;
+        return from_bytes_launch(c, s, din[0], dout[0], (uint8_t*)dout[1], cnt, zip216);
     });
 }
 

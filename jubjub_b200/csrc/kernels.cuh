@@ -640,6 +640,20 @@ __global__ void __launch_bounds__(128, 4) k_from_bytes(const char* __restrict__ 
     }
 }
 
+// AffinePoint -> ExtendedPoint (src/lib.rs:214-226): (u, v, 1, u, v).  Used between the decode and the scalar-mul
+// kernels of jj_scalar_mul_encoded.
+__global__ void __launch_bounds__(256) k_affine_to_extended(const char* __restrict__ in, char* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        aff_point a;
+        ext_point p;
+        ld_fe(a.u, in + i * 64);
+        ld_fe(a.v, in + i * 64 + 32);
+        point_from_affine(p, a);
+        st_ext(out, i, p);
+    }
+}
+
 // Builds the Fq square-root tables (fe.cuh) once per device: one thread, ~1 900 products.  status[0] = 1 when the
 // subgroup hash came out perfect.
 __global__ void k_fq_sqrt_init(uint32_t* status) {

@@ -207,6 +207,14 @@ class Engine:
         return self._call("jj_scalar_mul", [(points, EXT_W, np.uint64), sc], w, dt,
                           flags=f | flags | (L.JJ_SCALAR_MONT if scalar_mont else 0), out=out)
 
+    def scalar_mul_encoded(self, encodings, scalars, output="bytes", zip216=True):
+        """(out, ok): out[i] = [scalars[i]] AffinePoint::from_bytes(encodings[i]) -- wire format in (32-byte
+        encodings, src/lib.rs:455-464), decoded on the device (src/lib.rs:541-627); ok[i] = 0 for a rejected
+        encoding (its output unit is unspecified)."""
+        w, dt, f = self._out_fmt(output)
+        return self._call("jj_scalar_mul_encoded", [(encodings, 32, np.uint8), (scalars, 32, np.uint8)], w, dt,
+                          flags=f | (0 if zip216 else L.JJ_PRE_ZIP216), ok=True)
+
     def scalar_mul_fixed(self, base_affine, scalars, output="extended", scalar_mont=False, out=None):
         """out[i] = [scalars[i]] base  (`&AffinePoint * &Fr`, src/lib.rs:1109-1115), one shared base."""
         w, dt, f = self._out_fmt(output)

@@ -410,6 +410,38 @@ def test_batch_from_bytes_long_chains(eng, oracle):
     assert (got[ok == 1] == want[wok == 1]).all() and (got[ok == 0] == 0).all()
 
 
+def test_scalar_mul_encoded(eng, oracle):
+    """jj_scalar_mul_encoded: 32-byte encodings in, decode + scalar-mul on the device, every output format, host
+    buffers (several staged chunks) and device-resident; rejected encodings are flagged like batch_from_bytes."""
+    n = 150000
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 17, n))
+    k = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 18, n))
+    aff = eng.batch_normalize(eng.scalar_mul_fixed(oracle.generator(), t))
+    enc = eng.affine_to_bytes(aff).copy()
+    enc[11::37, 0] ^= 1        # mostly off the curve
+    enc[5::113] = 0xFF         # non-canonical
+    want_aff, wok = eng.batch_from_bytes(enc)     # decode parity itself is covered by test_batch_from_bytes*
+    ext = np.concatenate([want_aff, np.repeat(oracle.fe_one(FQ), n, axis=0), want_aff], axis=1)
+    want = eng.scalar_mul(ext, k, output="bytes")
+    got, ok = eng.scalar_mul_encoded(enc, k)
+    assert (ok == wok).all() and 0.9 * n < ok.sum() < n
+    assert (got[ok == 1] == want[ok == 1]).all()
+    # against the oracle end to end on a sample: decode -> ladder -> normalise -> encode
+    s = slice(0, 400)
+    oa, ook = oracle.batch_from_bytes(enc[s])
+    oext = np.concatenate([oa, np.repeat(oracle.fe_one(FQ), 400, axis=0), oa], axis=1)
+    owant = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(oext, k[s])))
+    assert (ok[s] == ook).all() and (got[s][ook == 1] == owant[ook == 1]).all()
+    for output in ("affine", "extended"):
+        g2, ok2 = eng.scalar_mul_encoded(enc[:5000], k[:5000], output=output)
+        a2 = g2 if output == "affine" else eng.batch_normalize(g2)
+        assert (ok2 == wok[:5000]).all()
+        assert (eng.affine_to_bytes(a2)[ok2 == 1] == want[:5000][ok2 == 1]).all()
+    gd, okd = eng.scalar_mul_encoded(eng.to_device(enc[:70000]), eng.to_device(k[:70000]))
+    assert (okd.download().ravel() == wok[:70000]).all()
+    assert (gd.download()[wok[:70000] == 1] == want[:70000][wok[:70000] == 1]).all()
+
+
 def test_is_torsion_free_large_batch_property(eng, oracle):
     """2^18 points P_i = [t_i] G with G of order 8r (src/lib.rs:1380-1396): P_i is torsion free exactly when
     8 | t_i (src/lib.rs:709-711) -- a size-independent check of the shared-scalar (width-5 NAF of r) kernel --
