@@ -34,6 +34,28 @@ def test_header_symbols_exported(built):
     assert sorted(_lib.ALL_SYMBOLS) == declared  # the Python binding covers the whole header
 
 
+def test_rust_shim_binds_the_whole_header():
+    """integration/rust (uncompiled reference text) declares every ABI symbol of the header, with the header's
+    argument counts, and the same flag / error constants."""
+    header = open(os.path.join(ROOT, "include", "jubjub_b200.h")).read()
+    rust = open(os.path.join(ROOT, "integration", "rust", "jubjub-b200", "src", "lib.rs")).read()
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(jj_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, re.S)}
+    decl.pop("jj_ctx", None)
+    bound = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (jj_[a-z0-9_]+)\(([^;]*?)\)\s*(?:->[^;]*)?;", rust, re.S)}
+    extra = {"jj_launch_count"}  # test / bench helper, not part of the documented surface
+    assert sorted(set(decl) - extra) == sorted(set(bound) - extra)
+    for name, args in decl.items():
+        if name in extra:
+            continue
+        n_c = 0 if args.strip() in ("", "void") else args.count(",") + 1
+        n_r = 0 if not bound[name].strip() else bound[name].count(",") + 1
+        assert n_c == n_r, (name, n_c, n_r)
+    for const, value in re.findall(r"\b(JJ_[A-Z0-9_]+)\s*=\s*([^,/\n]+)", header):
+        m = re.search(r"pub const %s: [iu]32 = ([^;]+);" % const, rust)
+        assert m, const
+        assert eval(m.group(1)) == eval(value.replace("u", "")), const
+
+
 def test_product_fails_loudly_without_gpu(built):
     import torch
 
