@@ -109,6 +109,23 @@ class Engine {
         check(jj_affine_to_bytes(ctx_, p.data(), out.data(), p.size(), 0));
         return out;
     }
+    // AffinePoint::batch_from_bytes (src/lib.rs:541-627): is_some[i] == 0 for a rejected encoding
+    std::vector<AffinePoint> batch_from_bytes(const std::vector<std::array<uint8_t, 32>>& enc, std::vector<uint8_t>& is_some) {
+        std::vector<AffinePoint> out(enc.size());
+        is_some.assign(enc.size(), 0);
+        check(jj_batch_from_bytes(ctx_, enc.data(), out.data(), is_some.data(), enc.size(), 0));
+        return out;
+    }
+    // wire format in and out: AffinePoint::from_bytes(enc[i]) * k[i], encoded (decode + scalar-mul + encode on the device)
+    std::vector<std::array<uint8_t, 32>> batch_mul_encoded(const std::vector<std::array<uint8_t, 32>>& enc,
+                                                           const std::vector<Fr>& k, std::vector<uint8_t>& is_some) {
+        same(enc.size(), k.size());
+        std::vector<std::array<uint8_t, 32>> out(enc.size());
+        is_some.assign(enc.size(), 0);
+        check(jj_scalar_mul_encoded(ctx_, enc.data(), k.data(), out.data(), is_some.data(), enc.size(),
+                                    JJ_SCALAR_MONT | JJ_OUT_BYTES));
+        return out;
+    }
     std::vector<uint8_t> batch_is_torsion_free(const std::vector<ExtendedPoint>& p) {
         std::vector<uint8_t> out(p.size());
         check(jj_is_torsion_free(ctx_, p.data(), out.data(), p.size(), 0));

@@ -34,6 +34,11 @@ int main(int argc, char** argv) {
         auto a = eng.batch_normalize(eng.batch_add(p, p));
         auto d = eng.batch_normalize(eng.batch_double(p));
         if (std::memcmp(a.data(), d.data(), n * sizeof(AffinePoint)) != 0) return 4;
+        // wire format in and out: encode p, then decode + multiply + encode on the device
+        std::vector<uint8_t> some;
+        auto enc2 = eng.batch_mul_encoded(eng.batch_to_bytes(eng.batch_normalize(p)), k, some);
+        for (uint64_t i = 0; i < n; i++)
+            if (!some[i] || std::memcmp(enc2[i].data(), want[i].data(), 32) != 0) return 7;
         bool threw = false;
         try {
             k.pop_back();
