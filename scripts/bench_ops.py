@@ -70,6 +70,9 @@ def main():
     flg = eng.empty((n, 1), np.uint8)
     rec("is_torsion_free", timed(eng, lambda: eng._check(eng.lib.jj_is_torsion_free(
         eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS)), reps=2, warm=1), 161)
+    outb = eng.empty((n, 32), np.uint8)
+    rec("scalar_mul_encoded (bytes->bytes)", timed(eng, lambda: eng._check(eng.lib.jj_scalar_mul_encoded(
+        eng.ctx, enc.ptr, k.ptr, outb.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS | jj.JJ_OUT_BYTES)), reps=2, warm=1), 97)
     # launch-bound chain: 48 small field batches (n = 4096) eagerly vs replayed as one CUDA graph
     m = 4096
     x, y, t2 = eng.fe_stream("fq", 1, m, device=True), eng.fe_stream("fq", 2, m, device=True), eng.empty((m, 4))
