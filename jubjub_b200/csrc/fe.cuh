@@ -147,6 +147,10 @@ JJ_DEVICE void fe_cadd_mod(uint32_t d[8], uint32_t cond) {
     JJ_ADDC_CC_I(d[6], d[6], F::M6); JJ_ADDC_I(d[7], d[7], F::M7);
 }
 template <class F>
+JJ_DEVICE void fe_cadd_mod_if_negative(uint32_t d[8], uint32_t cond) {
+    fe_cadd_mod<F>(d, cond >> 31);
+}
+template <class F>
 JJ_DEVICE void fe_csub_mod(uint32_t d[8], uint32_t cond) {
     if (!cond) return;
     JJ_SUB_CC_I(d[0], d[0], F::M0); JJ_SUBC_CC_I(d[1], d[1], F::M1); JJ_SUBC_CC_I(d[2], d[2], F::M2);
@@ -160,9 +164,9 @@ JJ_DEVICE void fe_cneg_mod(uint32_t d[8], uint32_t cond) {
     subc_cc(d[4], F::M4, d[4]); subc_cc(d[5], F::M5, d[5]); subc_cc(d[6], F::M6, d[6]); subc(d[7], F::M7, d[7]);
 }
 #else
-#define JJ_PRED8(OP0, OPC, OPL, SWAP)                                                                             \
+#define JJ_PRED8(SETP, OP0, OPC, OPL, SWAP)                                                                       \
     asm volatile(                                                                                                 \
-        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %8, 0;\n\t"                                                         \
+        "{\n\t.reg .pred p;\n\t" SETP " p, %8, 0;\n\t"                                                            \
         "@p " OP0 " %0, " SWAP("%0", "%9") ";\n\t@p " OPC " %1, " SWAP("%1", "%10") ";\n\t"                         \
         "@p " OPC " %2, " SWAP("%2", "%11") ";\n\t@p " OPC " %3, " SWAP("%3", "%12") ";\n\t"                        \
         "@p " OPC " %4, " SWAP("%4", "%13") ";\n\t@p " OPC " %5, " SWAP("%5", "%14") ";\n\t"                        \
@@ -173,15 +177,20 @@ JJ_DEVICE void fe_cneg_mod(uint32_t d[8], uint32_t cond) {
 #define JJ_ORD_MD(D, M) M ", " D
 template <class F>
 JJ_DEVICE void fe_cadd_mod(uint32_t d[8], uint32_t cond) {
-    JJ_PRED8("add.cc.u32", "addc.cc.u32", "addc.u32", JJ_ORD_DM);
+    JJ_PRED8("setp.ne.u32", "add.cc.u32", "addc.cc.u32", "addc.u32", JJ_ORD_DM);
+}
+// if ((int32_t)cond < 0) d += m: the sign test is the predicate itself (no shift)
+template <class F>
+JJ_DEVICE void fe_cadd_mod_if_negative(uint32_t d[8], uint32_t cond) {
+    JJ_PRED8("setp.lt.s32", "add.cc.u32", "addc.cc.u32", "addc.u32", JJ_ORD_DM);
 }
 template <class F>
 JJ_DEVICE void fe_csub_mod(uint32_t d[8], uint32_t cond) {
-    JJ_PRED8("sub.cc.u32", "subc.cc.u32", "subc.u32", JJ_ORD_DM);
+    JJ_PRED8("setp.ne.u32", "sub.cc.u32", "subc.cc.u32", "subc.u32", JJ_ORD_DM);
 }
 template <class F>
 JJ_DEVICE void fe_cneg_mod(uint32_t d[8], uint32_t cond) {
-    JJ_PRED8("sub.cc.u32", "subc.cc.u32", "subc.u32", JJ_ORD_MD);
+    JJ_PRED8("setp.ne.u32", "sub.cc.u32", "subc.cc.u32", "subc.u32", JJ_ORD_MD);
 }
 #endif
 
@@ -438,7 +447,7 @@ JJ_DEVICE void mont_finish_signed_fq(fe& r, const uint32_t E[8], const uint32_t 
 #pragma unroll
     for (int i = 1; i < 7; i++) addc_cc(s[i], O[i], E[i + 1]);
     addc(s[7], O[7], 0u);
-    fe_cadd_mod<FqP>(s, s[7] >> 31);
+    fe_cadd_mod_if_negative<FqP>(s, s[7]);
 #pragma unroll
     for (int i = 0; i < 8; i++) r.w[i] = s[i];
 }
