@@ -148,6 +148,41 @@ def test_emulated_field_arithmetic(emul, oracle, which):
     assert (emul.fe(which, 9, raw)[:, 0] == oracle.fe_from_bytes(which, raw.view(np.uint8).reshape(-1, 32))[1]).all()
 
 
+@pytest.mark.parametrize("which", [FQ, FR])
+def test_emulated_field_arithmetic_vs_bigint_fuzz(emul, which):
+    """Structured fuzzing of the kernel arithmetic source (host emulation) directly against Python big integers --
+    independent of the C oracle: values built from a few powers of two +- small offsets, limbs forced to 0 or
+    0xffffffff, neighbours of m, m/2, 2^k; every product / square formulation, add, sub, neg, double."""
+    from hypothesis import given, settings, strategies as st
+
+    m = M.Q if which == FQ else M.R_ORDER
+    rinv = pow(1 << 256, -1, m)
+    small = st.integers(-3, 3)
+    pw = st.integers(0, 255)
+    structured = st.builds(lambda ks, d, flip, base: (((sum(1 << k for k in ks) + d) ^ (flip * ((1 << 256) - 1))) + base) % m,
+                           st.lists(pw, min_size=0, max_size=4), small, st.integers(0, 1),
+                           st.sampled_from([0, m - 1, m >> 1, (m >> 1) + 1, m >> 225 << 224, (m >> 225 << 224) + (1 << 224)]))
+    limbs = st.builds(lambda ws: sum(w << (32 * i) for i, w in enumerate(ws)) % m,
+                      st.lists(st.sampled_from([0, 1, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF, 0x12345678]),
+                               min_size=8, max_size=8))
+    elem = st.one_of(structured, limbs, st.integers(0, m - 1))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(elem, elem), min_size=64, max_size=64))
+    def run(pairs):
+        a = np.array([M.limbs(x) for x, _ in pairs], dtype=np.uint64)
+        b = np.array([M.limbs(y) for _, y in pairs], dtype=np.uint64)
+        want = {0: lambda x, y: x * y * rinv % m, 1: lambda x, y: x * x * rinv % m, 2: lambda x, y: (x + y) % m,
+                3: lambda x, y: (x - y) % m, 4: lambda x, y: -x % m, 5: lambda x, y: 2 * x % m,
+                10: lambda x, y: x * y * rinv % m, 11: lambda x, y: x * x * rinv % m}
+        for op, f in want.items():
+            got = emul.fe(which, op, a, b)
+            for i, (x, y) in enumerate(pairs):
+                assert M.from_limbs(got[i]) == f(x, y), (op, hex(x), hex(y))
+
+    run()
+
+
 def test_emulated_points_and_scalar_mul(emul, oracle):
     n = 48
     g = oracle.affine_to_extended(oracle.generator())
