@@ -14,7 +14,6 @@ There is no CPU arithmetic here: without a B200 the engine constructor raises.
 """
 import numpy as np
 
-from . import _lib as L
 from .engine import default_engine
 
 _GEN_RAW = (0x62EDCBB8BF3787C88B0F03DDD60A8187CAF55D1B29BF81AFE4B3D35DF1A7ADFE, 11)  # src/lib.rs:1380-1396

@@ -3,7 +3,6 @@ Writes gpurun_out/probe.json.  Not a bench line (bench.py is); used to pick defa
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402

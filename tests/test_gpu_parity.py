@@ -8,7 +8,7 @@ import pytest
 
 from oracle import model as M
 from tests.golden import reference_kats as K
-from tests.helpers import affine_raw, b32, edge_field_pairs, fe, fe_int, scalar_bytes
+from tests.helpers import affine_raw, b32, edge_field_pairs, fe, scalar_bytes
 
 pytestmark = pytest.mark.gpu
 
