@@ -13,6 +13,7 @@
 #include <mutex>
 #include <initializer_list>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -527,21 +528,23 @@ int32_t jj_init(int device, jj_ctx** out) {
         jj_destroy(c);
         return JJ_ERR_CUDA;
     }
-    {   // device-resident tables of the table-driven Fq square root (decode path): built once per device and
-        // process -- a second context must not rewrite them under a kernel of the first
+    {   // device-resident tables of the table-driven Fq square root (decode path): built once per device -- a
+        // second context must not rewrite them under a kernel of the first.  Whether they are there is read
+        // from the device itself (the `ready` word of the table), so a cudaDeviceReset in between is noticed.
         static std::mutex mu;
-        static bool built[256] = {false};
         std::lock_guard<std::mutex> lock(mu);
-        uint32_t* st = nullptr;
-        uint32_t host = 0;
-        const bool need = device >= 256 || !built[device];
-        ok = !need || cudaMalloc(&st, sizeof(uint32_t)) == cudaSuccess;
-        if (ok && need) {
-            k_fq_sqrt_init<<<1, 32, 0, c->stream>>>(st);
-            ok = cudaMemcpyAsync(&host, st, sizeof(host), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
-                 cudaStreamSynchronize(c->stream) == cudaSuccess && host == 1u;
-            cudaFree(st);
-            if (ok && device < 256) built[device] = true;
+        uint32_t ready = 0;
+        ok = cudaMemcpyFromSymbol(&ready, g_fq_sqrt_tab, sizeof(ready), offsetof(FqSqrtTables, ready)) == cudaSuccess;
+        if (ok && ready != 1u) {
+            uint32_t* st = nullptr;
+            uint32_t host = 0;
+            ok = cudaMalloc(&st, sizeof(uint32_t)) == cudaSuccess;
+            if (ok) {
+                k_fq_sqrt_init<<<1, 32, 0, c->stream>>>(st);
+                ok = cudaMemcpyAsync(&host, st, sizeof(host), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                     cudaStreamSynchronize(c->stream) == cudaSuccess && host == 1u;
+                cudaFree(st);
+            }
         }
         if (!ok) {
             jj_destroy(c);
