@@ -174,7 +174,6 @@ const SmulVariant kVariants[] = {
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
-constexpr int kLargeBatchVariant = 24;
 
 template <int T, int MB, int TAB>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
@@ -211,10 +210,6 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
                     uint8_t* flag_out, size_t n, char** tbl, size_t* tbl_cap, bool scalar_mont,
                     const PeerOut* peers = nullptr) {
     int v = c->smul_variant > 0 && c->smul_variant < kNumVariants ? c->smul_variant : kDefaultVariant;
-    // Library default: 16 warps/SM (mapping 13); batches of at least four 24-warp rounds run the 24-warp mapping,
-    // measured 1.3 % faster on resident batches.  Staged host chunks are one 16-warp round
-    // and stay on mapping 13.
-    if (c->smul_variant <= 0 && n >= (size_t)4 * c->sm_count * kVariants[kLargeBatchVariant].threads) v = kLargeBatchVariant;
     SmulArgs a{};
     a.points = pts;
     a.scalars = sc;
