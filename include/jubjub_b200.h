@@ -68,7 +68,11 @@ enum {
     JJ_SCALAR_MONT = 1u << 4,
     JJ_OUT_AFFINE = 1u << 5, /* scalar-mul writes normalised AffinePoint (64 B) instead of Extended */
     JJ_OUT_BYTES = 1u << 6,  /* scalar-mul writes the 32-byte encoding (src/lib.rs:455-464)      */
-    JJ_PRE_ZIP216 = 1u << 7  /* jj_batch_from_bytes: from_bytes_pre_zip216_compatibility (src/lib.rs:485-490) */
+    JJ_PRE_ZIP216 = 1u << 7, /* jj_batch_from_bytes: from_bytes_pre_zip216_compatibility (src/lib.rs:485-490) */
+    JJ_CHECK_SUBGROUP = 1u << 8, /* jj_scalar_mul_encoded: ok[i] also requires is_torsion_free, i.e. the decode is
+                                    SubgroupPoint::from_bytes (src/lib.rs:1427-1429) */
+    JJ_TORSION_LADDER = 1u << 9  /* jj_is_torsion_free: decide by the reference's own [r]P == O (src/lib.rs:709-711)
+                                    instead of the pairing test -- same flags, ~7x the work; the cross-check */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -78,7 +82,9 @@ int32_t jj_sync(jj_ctx* ctx);
 const char* jj_last_error(const jj_ctx* ctx);
 const char* jj_version(void);
 int32_t jj_device_info(jj_ctx* ctx, int32_t* sm_count, int32_t* sm_clock_khz, uint64_t* hbm_bytes);
-/* Tuning knob for the variable-base kernel variant; 0 = library default. */
+/* Tuning knob; 0 = library defaults.  13 / 24 / 5: variable-base kernel with 16 / 24 / 8 warps
+ * per SM; 100: fixed-base kernel with 4-bit windows; 200 / 201: converted outputs of device-resident variable-base
+ * batches always / never use the kernel's fused normalise epilogue (default: from 4 rounds of resident threads up). */
 int32_t jj_set_scalar_mul_variant(jj_ctx* ctx, int32_t variant);
 /* Number of this library's kernel launches issued on ctx so far (bench.py's gpu_launches). */
 uint64_t jj_launch_count(const jj_ctx* ctx);
@@ -97,7 +103,14 @@ int32_t jj_flush_l2(jj_ctx* ctx); /* overwrites a scratch buffer larger than L2 
 /* CUDA graphs for launch-bound sequences (many small field/point batches): between jj_graph_begin and
  * jj_graph_end every call made with JJ_DEVICE_PTRS | JJ_ASYNC is captured on the context's stream instead of
  * executed; jj_graph_launch replays the whole sequence with one launch (ordered on the stream, jj_sync waits).
- * Scratch buffers must already exist: run the sequence once eagerly before capturing it. */
+ * Rules (violations return JJ_ERR_INVALID_ARG, nothing is corrupted):
+ *  - scratch buffers must already exist and be large enough: run the sequence once eagerly before capturing it --
+ *    a captured call that would have to allocate fails, and so does any other call inside a capture that is not
+ *    JJ_DEVICE_PTRS | JJ_ASYNC (host-pointer calls synchronise), jj_scalar_mul_fixed (its table cache is checked on
+ *    the host) and jj_scalar_mul_sharded;
+ *  - a captured graph holds the scratch pointers of its kernels, so while any graph of this context is alive
+ *    (until jj_graph_destroy) a call that would have to GROW a scratch buffer of the main stream fails instead of
+ *    reallocating it: run the largest batch first, or destroy the graphs. */
 int32_t jj_graph_begin(jj_ctx* ctx);
 int32_t jj_graph_end(jj_ctx* ctx, void** graph_exec);
 int32_t jj_graph_launch(jj_ctx* ctx, void* graph_exec);
@@ -172,9 +185,15 @@ int32_t jj_scalar_mul_encoded(jj_ctx* ctx, const void* points32, const void* sca
 /* out[i] = [scalars[i]] base: `&AffinePoint * &Fr` src/lib.rs:1109-1115 -> AffineNielsPoint::multiply :271-295,
  * one shared base; the per-window AffineNiels table is built once per base and cached in ctx. */
 int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* scalars32, void* out, size_t n, uint32_t flags);
-/* batch_normalize src/lib.rs:840-858 / :1084-1107: ExtendedPoint -> AffinePoint (z = 0 gives (0, 0)
+/* ExtendedPoint::mul_by_cofactor src/lib.rs:722-724 (= double().double().double(), all 160 B bit-exact) */
+int32_t jj_mul_by_cofactor(jj_ctx* ctx, const void* p_ext, void* out_ext, size_t n, uint32_t flags);
+/* ExtendedPoint::batch_normalize src/lib.rs:840-858: ExtendedPoint -> AffinePoint (z = 0 gives (0, 0)
  * like ff::BatchInverter's skipped zeros) */
 int32_t jj_batch_normalize(jj_ctx* ctx, const void* in_ext, void* out_affine, size_t n, uint32_t flags);
+/* The free function batch_normalize src/lib.rs:1084-1107: normalises the ExtendedPoints themselves,
+ * (u, v, z, t1, t2) -> (u/z, v/z, 1, u/z, v/z) ((0, 0, 1, 0, 0) for z = 0); out_ext may be in_ext (in place, as the
+ * reference's `&mut [ExtendedPoint]`); the affine points are the first 64 bytes of every output unit. */
+int32_t jj_batch_normalize_extended(jj_ctx* ctx, const void* in_ext, void* out_ext, size_t n, uint32_t flags);
 /* AffinePoint::to_bytes src/lib.rs:455-464 */
 int32_t jj_affine_to_bytes(jj_ctx* ctx, const void* in_affine, void* out32, size_t n, uint32_t flags);
 /* AffinePoint::batch_from_bytes src/lib.rs:541-627 (per element: from_bytes_inner :492-534): 32-byte
@@ -182,9 +201,12 @@ int32_t jj_affine_to_bytes(jj_ctx* ctx, const void* in_affine, void* out32, size
  * non-canonical encoding of (0, +-1).  JJ_PRE_ZIP216 accepts the latter like
  * from_bytes_pre_zip216_compatibility (:485-490). */
 int32_t jj_batch_from_bytes(jj_ctx* ctx, const void* in32, void* out_affine, uint8_t* ok, size_t n, uint32_t flags);
-/* ExtendedPoint::is_torsion_free src/lib.rs:709-711 ([r]P == identity), is_identity :691-696,
- * is_small_order :699-705; flags_out[i] in {0, 1} */
+/* ExtendedPoint::is_torsion_free src/lib.rs:709-711 ([r]P == identity; decided by the order-8 Tate pairing with the
+ * 8-torsion point, one 223-bit power instead of a scalar multiplication -- same booleans, csrc/torsion.cuh),
+ * is_prime_order :717-719 (torsion free and not the identity), is_identity :691-696, is_small_order :699-705;
+ * flags_out[i] in {0, 1} */
 int32_t jj_is_torsion_free(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
+int32_t jj_is_prime_order(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
 int32_t jj_is_identity(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
 int32_t jj_is_small_order(jj_ctx* ctx, const void* p_ext, uint8_t* flags_out, size_t n, uint32_t flags);
 
@@ -196,16 +218,28 @@ int32_t jj_comm_init(jj_ctx* ctx, int32_t nranks, int32_t rank, const void* id12
 int32_t jj_comm_destroy(jj_ctx* ctx);
 /* Computes this rank's shard of out = [scalars] points (shard-local device inputs of n_local units)
  * and all-gathers the results: out_all (device, nranks * n_local units) holds every rank's outputs
- * in rank order.  Output unit = ExtendedPoint, or per JJ_OUT_AFFINE / JJ_OUT_BYTES. */
+ * in rank order.  Output unit = ExtendedPoint, or per JJ_OUT_AFFINE / JJ_OUT_BYTES.  Equal n_local on all ranks. */
 int32_t jj_scalar_mul_sharded(jj_ctx* ctx, const void* points_ext_local, const void* scalars32_local,
                               void* out_all, size_t n_local, uint32_t flags);
+/* The same for a batch of n_total units that need not divide evenly: rank g of G owns the block
+ * [g*n_total/G, (g+1)*n_total/G) (blocks differ by at most one unit; ragged blocks are gathered by one ncclBroadcast
+ * per rank in a group).  points/scalars hold this rank's block only.  Without JJ_DEVICE_PTRS the two INPUTS are host
+ * buffers, staged in round-sized chunks that overlap the kernels; out_all is always the device-resident gathered
+ * buffer.  out_local_host (may be NULL): this rank's own block of results is also copied to that host buffer. */
+int32_t jj_scalar_mul_sharded_n(jj_ctx* ctx, const void* points_ext_local, const void* scalars32_local,
+                                void* out_all, void* out_local_host, size_t n_total, uint32_t flags);
 
 /* Fused compute + all-gather over NVLink peer memory.  Each rank exports its gathered-output buffer
  * (jj_ipc_export -> 64-byte cudaIpcMemHandle), the host exchanges the handles, every rank opens its
  * peers' buffers (jj_ipc_open) and registers the nranks pointers in rank order (own pointer at index
- * rank).  jj_scalar_mul_sharded with ExtendedPoint output then stores every result straight into all
- * ranks' buffers from the scalar-mul kernel's epilogue (P2P stores) and ends with a 4-byte
- * stream-ordered NCCL rendezvous instead of a separate ncclAllGather. */
+ * rank).  jj_scalar_mul_sharded then stores every result -- ExtendedPoint, or with JJ_OUT_AFFINE / JJ_OUT_BYTES the
+ * normalised point / its 32-byte encoding produced by the kernel's fused normalise epilogue -- straight into all
+ * ranks' buffers from the scalar-mul kernel (P2P stores), bracketed by two 4-byte stream-ordered NCCL rendezvous
+ * instead of a separate ncclAllGather.  Ordering contract: the call may overwrite EVERY rank's registered buffer, and
+ * it starts doing so only after all ranks have entered it (leading rendezvous).  So a rank must be done reading its own
+ * copy of out_all (work ordered before the call on the context's stream, or finished on the host) before IT calls
+ * again; it need not know what its peers are doing.  When the call has completed on a rank (stream order / jj_sync)
+ * all peers' stores into that rank's buffer have landed (trailing rendezvous). */
 int32_t jj_ipc_export(jj_ctx* ctx, const void* dptr, void* handle64);
 int32_t jj_ipc_open(jj_ctx* ctx, const void* handle64, void** dptr);
 int32_t jj_ipc_close(jj_ctx* ctx, void* dptr);

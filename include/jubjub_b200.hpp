@@ -64,15 +64,17 @@ class Engine {
     }
 
     // ---- points
+    // The scalar multiplications are variable-time in the scalar (the reference's `*` is constant-time by policy,
+    // src/lib.rs:12-17) and are named *_vartime after the reference's rule (src/lib.rs:14-15): public scalars only.
     // `&ExtendedPoint * &Fr` element-wise (src/lib.rs:873-879)
-    std::vector<ExtendedPoint> batch_mul(const std::vector<ExtendedPoint>& p, const std::vector<Fr>& k) {
+    std::vector<ExtendedPoint> batch_mul_vartime(const std::vector<ExtendedPoint>& p, const std::vector<Fr>& k) {
         same(p.size(), k.size());
         std::vector<ExtendedPoint> out(p.size());
         check(jj_scalar_mul(ctx_, p.data(), k.data(), out.data(), p.size(), JJ_SCALAR_MONT));
         return out;
     }
     // `&AffinePoint * &Fr` for one shared base (src/lib.rs:1109-1115)
-    std::vector<ExtendedPoint> batch_mul_fixed(const AffinePoint& base, const std::vector<Fr>& k) {
+    std::vector<ExtendedPoint> batch_mul_fixed_vartime(const AffinePoint& base, const std::vector<Fr>& k) {
         std::vector<ExtendedPoint> out(k.size());
         check(jj_scalar_mul_fixed(ctx_, &base, k.data(), out.data(), k.size(), JJ_SCALAR_MONT));
         return out;
@@ -117,7 +119,7 @@ class Engine {
         return out;
     }
     // wire format in and out: AffinePoint::from_bytes(enc[i]) * k[i], encoded (decode + scalar-mul + encode on the device)
-    std::vector<std::array<uint8_t, 32>> batch_mul_encoded(const std::vector<std::array<uint8_t, 32>>& enc,
+    std::vector<std::array<uint8_t, 32>> batch_mul_encoded_vartime(const std::vector<std::array<uint8_t, 32>>& enc,
                                                            const std::vector<Fr>& k, std::vector<uint8_t>& is_some) {
         same(enc.size(), k.size());
         std::vector<std::array<uint8_t, 32>> out(enc.size());
@@ -126,9 +128,28 @@ class Engine {
                                     JJ_SCALAR_MONT | JJ_OUT_BYTES));
         return out;
     }
+    // is_torsion_free / is_prime_order (src/lib.rs:709-719), mul_by_cofactor (:722-724)
     std::vector<uint8_t> batch_is_torsion_free(const std::vector<ExtendedPoint>& p) {
         std::vector<uint8_t> out(p.size());
         check(jj_is_torsion_free(ctx_, p.data(), out.data(), p.size(), 0));
+        return out;
+    }
+    std::vector<uint8_t> batch_is_prime_order(const std::vector<ExtendedPoint>& p) {
+        std::vector<uint8_t> out(p.size());
+        check(jj_is_prime_order(ctx_, p.data(), out.data(), p.size(), 0));
+        return out;
+    }
+    std::vector<ExtendedPoint> batch_mul_by_cofactor(const std::vector<ExtendedPoint>& p) {
+        std::vector<ExtendedPoint> out(p.size());
+        check(jj_mul_by_cofactor(ctx_, p.data(), out.data(), p.size(), 0));
+        return out;
+    }
+    // the free function batch_normalize (src/lib.rs:1084-1107): normalises `p` in place (z = 1, t1 = u, t2 = v)
+    // and returns the affine points
+    std::vector<AffinePoint> batch_normalize_in_place(std::vector<ExtendedPoint>& p) {
+        check(jj_batch_normalize_extended(ctx_, p.data(), p.data(), p.size(), 0));
+        std::vector<AffinePoint> out(p.size());
+        for (size_t i = 0; i < p.size(); i++) out[i] = AffinePoint{p[i].u, p[i].v};
         return out;
     }
 

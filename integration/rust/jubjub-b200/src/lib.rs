@@ -53,6 +53,8 @@ pub const JJ_SCALAR_MONT: u32 = 1 << 4;
 pub const JJ_OUT_AFFINE: u32 = 1 << 5;
 pub const JJ_OUT_BYTES: u32 = 1 << 6;
 pub const JJ_PRE_ZIP216: u32 = 1 << 7;
+pub const JJ_CHECK_SUBGROUP: u32 = 1 << 8;
+pub const JJ_TORSION_LADDER: u32 = 1 << 9;
 
 #[link(name = "jubjub_b200")]
 extern "C" {
@@ -115,10 +117,13 @@ extern "C" {
     pub fn jj_scalar_mul(ctx: *mut JjCtx, points_ext: *const c_void, scalars32: *const c_void, out: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_scalar_mul_encoded(ctx: *mut JjCtx, points32: *const c_void, scalars32: *const c_void, out: *mut c_void, ok: *mut u8, n: usize, flags: u32) -> i32;
     pub fn jj_scalar_mul_fixed(ctx: *mut JjCtx, base_affine: *const c_void, scalars32: *const c_void, out: *mut c_void, n: usize, flags: u32) -> i32;
+    pub fn jj_mul_by_cofactor(ctx: *mut JjCtx, p_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_batch_normalize(ctx: *mut JjCtx, in_ext: *const c_void, out_affine: *mut c_void, n: usize, flags: u32) -> i32;
+    pub fn jj_batch_normalize_extended(ctx: *mut JjCtx, in_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_affine_to_bytes(ctx: *mut JjCtx, in_affine: *const c_void, out32: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_batch_from_bytes(ctx: *mut JjCtx, in32: *const c_void, out_affine: *mut c_void, ok: *mut u8, n: usize, flags: u32) -> i32;
     pub fn jj_is_torsion_free(ctx: *mut JjCtx, p_ext: *const c_void, flags_out: *mut u8, n: usize, flags: u32) -> i32;
+    pub fn jj_is_prime_order(ctx: *mut JjCtx, p_ext: *const c_void, flags_out: *mut u8, n: usize, flags: u32) -> i32;
     pub fn jj_is_identity(ctx: *mut JjCtx, p_ext: *const c_void, flags_out: *mut u8, n: usize, flags: u32) -> i32;
     pub fn jj_is_small_order(ctx: *mut JjCtx, p_ext: *const c_void, flags_out: *mut u8, n: usize, flags: u32) -> i32;
 
@@ -127,6 +132,7 @@ extern "C" {
     pub fn jj_comm_init(ctx: *mut JjCtx, nranks: i32, rank: i32, id128: *const c_void) -> i32;
     pub fn jj_comm_destroy(ctx: *mut JjCtx) -> i32;
     pub fn jj_scalar_mul_sharded(ctx: *mut JjCtx, points_ext_local: *const c_void, scalars32_local: *const c_void, out_all: *mut c_void, n_local: usize, flags: u32) -> i32;
+    pub fn jj_scalar_mul_sharded_n(ctx: *mut JjCtx, points_ext_local: *const c_void, scalars32_local: *const c_void, out_all: *mut c_void, out_local_host: *mut c_void, n_total: usize, flags: u32) -> i32;
     pub fn jj_ipc_export(ctx: *mut JjCtx, dptr: *const c_void, handle64: *mut c_void) -> i32;
     pub fn jj_ipc_open(ctx: *mut JjCtx, handle64: *const c_void, dptr: *mut *mut c_void) -> i32;
     pub fn jj_ipc_close(ctx: *mut JjCtx, dptr: *mut c_void) -> i32;
@@ -322,10 +328,14 @@ impl Engine {
     }
 }
 
-/// Inside a fork of the reference crate the private limbs are visible and no conversion is needed:
-/// `ExtendedPoint` is five `Fq` = 5 x `[u64; 4]` Montgomery limbs in declaration order (`src/lib.rs:139-145`),
-/// byte-identical to the ABI's 160-byte unit, and `Fr(pub(crate) [u64; 4])` (`src/fr.rs:23`) is the
-/// `JJ_SCALAR_MONT` scalar.  The in-crate entry point is then one call:
+/// Inside a fork of the reference crate `Fr(pub(crate) [u64; 4])` (`src/fr.rs:23`) is visible and is exactly the
+/// `JJ_SCALAR_MONT` scalar.  `Fq` is NOT: it is `bls12_381::Scalar` (`src/lib.rs:62`), whose limbs are private even to a
+/// fork of jubjub, and whose struct layout Rust does not specify (no `#[repr(C)]` / `#[repr(transparent)]` upstream).
+/// `ExtendedPoint` is five of them in declaration order (`src/lib.rs:139-145`); in practice that is 5 x `[u64; 4]`
+/// Montgomery limbs, byte-identical to the ABI's 160-byte unit, but the pointer cast below RELIES ON UNSPECIFIED LAYOUT.
+/// A fork that wants it to be sound must also vendor `bls12_381` with `#[repr(transparent)]` on `Scalar` (and lift the
+/// crate's `#![deny(unsafe_code)]`, `src/lib.rs:24`, for this one module), or stay on the wire-format path above.
+/// With that caveat, the in-crate entry point is one call:
 ///
 /// ```ignore
 /// impl ExtendedPoint {

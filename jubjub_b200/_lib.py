@@ -21,6 +21,8 @@ JJ_SCALAR_MONT = 1 << 4
 JJ_OUT_AFFINE = 1 << 5
 JJ_OUT_BYTES = 1 << 6
 JJ_PRE_ZIP216 = 1 << 7
+JJ_CHECK_SUBGROUP = 1 << 8
+JJ_TORSION_LADDER = 1 << 9
 
 ERRORS = {0: "JJ_OK", -1: "JJ_ERR_INVALID_ARG", -2: "JJ_ERR_CUDA", -3: "JJ_ERR_NCCL", -4: "JJ_ERR_OOM",
           -5: "JJ_ERR_NO_DEVICE"}
@@ -54,11 +56,13 @@ PROTOTYPES = {
     "jj_point_add_affine_niels": _BINARY, "jj_point_to_niels": _UNARY, "jj_affine_to_niels": _UNARY,
     "jj_scalar_mul": _BINARY, "jj_scalar_mul_fixed": _BINARY,
     "jj_scalar_mul_encoded": [_vp, _vp, _vp, _vp, _sz, _u32],
-    "jj_batch_normalize": _UNARY, "jj_affine_to_bytes": _UNARY,
+    "jj_batch_normalize": _UNARY, "jj_batch_normalize_extended": _UNARY, "jj_affine_to_bytes": _UNARY,
+    "jj_mul_by_cofactor": _UNARY, "jj_is_prime_order": _UNARY,
     "jj_batch_from_bytes": _WITH_OK,
     "jj_is_torsion_free": _UNARY, "jj_is_identity": _UNARY, "jj_is_small_order": _UNARY,
     "jj_comm_init": [_i32, _i32, _vp], "jj_comm_destroy": [],
     "jj_scalar_mul_sharded": [_vp, _vp, _vp, _sz, _u32],
+    "jj_scalar_mul_sharded_n": [_vp, _vp, _vp, _vp, _sz, _u32],
     "jj_ipc_export": [_vp, _vp], "jj_ipc_open": [_vp, C.POINTER(_vp)], "jj_ipc_close": [_vp],
     "jj_comm_set_peer_outputs": [C.POINTER(_vp), _i32],
 }

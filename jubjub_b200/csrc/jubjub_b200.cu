@@ -48,6 +48,9 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -63,9 +66,14 @@ bool load_nccl() {
         g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
         g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
         g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+        g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclBroadcast");
+        g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+        g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
         g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
         g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-        if (g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy) {
+        // every entry point the library calls must resolve: a partial libnccl is treated as absent
+        if (g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.Broadcast &&
+            g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.CommDestroy) {
             g_nccl.handle = h;
             return true;
         }
@@ -88,6 +96,11 @@ struct jj_ctx {
     size_t tmp_cap = 0;
     char* tmp2 = nullptr;
     size_t tmp2_cap = 0;
+    char* norm = nullptr;  // scratch of the fused normalise epilogue (k_scalar_mul<.., NORM>)
+    size_t norm_cap = 0;
+    int live_graphs = 0;  // graphs captured on this context and not yet destroyed: their nodes hold scratch pointers
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[kStages] = {nullptr, nullptr};
     uint32_t* fixed_table = nullptr;  // 64*8*24 words
     char* fixed_base_dev = nullptr;   // 64 B
     char fixed_base_key[64];
@@ -122,8 +135,28 @@ int32_t fail(jj_ctx* c, int32_t code, const char* fmt, ...) {
                         cudaGetErrorString(e_));                                                 \
     } while (0)
 
-int32_t ensure(jj_ctx* c, char** buf, size_t* cap, size_t bytes) {
+bool capturing(jj_ctx* c) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(c->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
+// Grows a scratch buffer.  Buffers used by calls on the context's main stream can be baked into captured
+// graphs (jj_graph_*): they are never reallocated while a capture is in progress (cudaMalloc / cudaFree are
+// illegal there) or while a captured graph is alive (its kernel nodes would write through the stale pointer).
+int32_t ensure(jj_ctx* c, char** buf, size_t* cap, size_t bytes, bool main_scratch = true) {
     if (*cap >= bytes && *buf) return JJ_OK;
+    if (!main_scratch) {  // staging-stream buffers: host-pointer calls are never captured
+        if (*buf) CU(c, cudaFree(*buf));
+        *buf = nullptr;
+        *cap = 0;
+        CU(c, cudaMalloc((void**)buf, bytes));
+        *cap = bytes;
+        return JJ_OK;
+    }
+    if (capturing(c))
+        return fail(c, JJ_ERR_INVALID_ARG, "scratch would have to grow during graph capture: run the sequence once eagerly first");
+    if (c->live_graphs > 0)
+        return fail(c, JJ_ERR_INVALID_ARG, "scratch would be reallocated while %d captured graph(s) still refer to it: "
+                    "destroy them (jj_graph_destroy) or run the larger batch before capturing", c->live_graphs);
     if (*buf) CU(c, cudaFree(*buf));
     *buf = nullptr;
     *cap = 0;
@@ -138,46 +171,46 @@ int grid_for(const jj_ctx* c, size_t n, int threads, int blocks_per_sm) {
     return (int)std::max<size_t>(1, std::min(need, cap));
 }
 
-// ---- scalar-mul variants (jj_set_scalar_mul_variant) -------------------------------------------
+// ---- scalar-mul mappings (jj_set_scalar_mul_variant) --------------------------------------------
+// The default build ships the default mapping and two A/B mappings; the experiments of round 1 (shared-memory
+// tables, the slot-file kernel, other block shapes; all measured slower) compile only
+// with -DJJ_EXPERIMENTS.
 struct SmulVariant {
-    int threads, min_blocks, table;
+    int id, threads, min_blocks, table;
 };
 const SmulVariant kVariants[] = {
-    {0, 0, 0},                 // 0: default -> kDefaultVariant
-    {224, 1, TABLE_SMEM},      // 1: 7 warps/SM, table in 224 KB of shared memory
-    {128, 2, TABLE_GMEM},      // 2: 8 warps/SM, table in L2-resident global scratch
-    {128, 3, TABLE_GMEM},      // 3: 12 warps/SM
-    {128, 4, TABLE_GMEM},      // 4: 16 warps/SM (<= 128 registers)
-    {256, 1, TABLE_GMEM},      // 5: 8 warps/SM in one block
-    {192, 1, TABLE_SMEM},      // 6: 6 warps/SM, shared memory
-    {128, 1, TABLE_SMEM},      // 7: 4 warps/SM, shared memory (one block of 128 KB)
-    {64, 3, TABLE_SMEM},       // 8: 3 blocks x 2 warps, shared memory
-    {96, 4, TABLE_GMEM},       // 9: 12 warps/SM in 4 blocks
-    {64, 6, TABLE_GMEM},       // 10: 12 warps/SM in 6 blocks
-    {384, 1, TABLE_GMEM},      // 11: 12 warps/SM in one block
-    {192, 2, TABLE_GMEM},      // 12: 12 warps/SM in two blocks
-    {512, 1, TABLE_GMEM},      // 13: 16 warps/SM in one block (<= 128 registers)
-    {320, 1, TABLE_GMEM},      // 14: 10 warps/SM
-    {512, 1, 2},               // 15: slot-file mapping (slotmul.cuh), 16 warps/SM
-    {384, 1, 2},               // 16: slot-file, 12 warps/SM
-    {544, 1, 2},               // 17: slot-file, 17 warps/SM (226 KB of shared memory)
-    {256, 2, 2},               // 18: slot-file, 2 x 8 warps/SM
-    {448, 1, TABLE_GMEM},      // 19: 14 warps/SM (<= 146 registers)
-    {480, 1, TABLE_GMEM},      // 20: 15 warps/SM (<= 136 registers)
-    {256, 2, TABLE_GMEM},      // 21: 16 warps/SM in two blocks (<= 128 registers)
-    {576, 1, TABLE_GMEM},      // 22: 18 warps/SM (<= 113 registers, spills)
-    {640, 1, TABLE_GMEM},      // 23: 20 warps/SM (<= 96 registers: spill code only around the additions)
-    {768, 1, TABLE_GMEM},      // 24: 24 warps/SM (<= 80 registers)
-    {704, 1, TABLE_GMEM},      // 25: 22 warps/SM (<= 88 registers)
-    {896, 1, TABLE_GMEM},      // 26: 28 warps/SM (<= 72 registers)
-    {1024, 1, TABLE_GMEM},     // 27: 32 warps/SM (<= 64 registers)
+    {13, 512, 1, TABLE_GMEM},  // default: 16 warps/SM in one block (<= 128 registers), table in L2-resident scratch
+    {24, 768, 1, TABLE_GMEM},  // 24 warps/SM (<= 80 registers): +1.3 % on resident batches, but its tables leave L2
+    {5, 256, 1, TABLE_GMEM},   // 8 warps/SM (<= 255 registers)
+#if defined(JJ_EXPERIMENTS)
+    {1, 224, 1, TABLE_SMEM},  {2, 128, 2, TABLE_GMEM},  {3, 128, 3, TABLE_GMEM},  {4, 128, 4, TABLE_GMEM},
+    {6, 192, 1, TABLE_SMEM},  {7, 128, 1, TABLE_SMEM},  {8, 64, 3, TABLE_SMEM},   {9, 96, 4, TABLE_GMEM},
+    {10, 64, 6, TABLE_GMEM},  {11, 384, 1, TABLE_GMEM}, {12, 192, 2, TABLE_GMEM}, {14, 320, 1, TABLE_GMEM},
+    {15, 512, 1, 2},          {16, 384, 1, 2},          {17, 544, 1, 2},          {18, 256, 2, 2},
+    {19, 448, 1, TABLE_GMEM}, {20, 480, 1, TABLE_GMEM}, {21, 256, 2, TABLE_GMEM}, {22, 576, 1, TABLE_GMEM},
+    {23, 640, 1, TABLE_GMEM}, {25, 704, 1, TABLE_GMEM}, {26, 896, 1, TABLE_GMEM}, {27, 1024, 1, TABLE_GMEM},
+#endif
 };
-constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 13;
+// knob values outside the mapping table
+constexpr int kFixedW4 = 100;         // fixed-base kernel with 4-bit windows (47 KB table)
+constexpr int kFusedNormOn = 200;     // converted outputs: always use the fused normalise epilogue (k_scalar_mul<.., NORM>)
+constexpr int kFusedNormOff = 201;    // ... never (separate k_batch_normalize pass)
 
-template <int T, int MB, int TAB>
+const SmulVariant& smul_variant(const jj_ctx* c) {
+    for (const SmulVariant& v : kVariants)
+        if (v.id == c->smul_variant) return v;
+    return kVariants[0];
+}
+// units one launch keeps resident (one per thread): host batches are staged in whole multiples of it
+size_t smul_round(const jj_ctx* c) {
+    const SmulVariant& v = smul_variant(c);
+    return (size_t)c->sm_count * v.threads * v.min_blocks;
+}
+
+template <int T, int MB, int TAB, bool NORM>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
-    auto kern = k_scalar_mul<T, MB, TAB>;
+    auto kern = k_scalar_mul<T, MB, TAB, NORM>;
     size_t smem = TAB == TABLE_SMEM ? (size_t)(T / 32) * 32768 : 0;
     int grid = grid_for(c, a.n, T, MB);
     if (TAB == TABLE_SMEM) {
@@ -192,6 +225,7 @@ int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t*
     CU(c, cudaGetLastError());
     return JJ_OK;
 }
+#if defined(JJ_EXPERIMENTS)
 template <int T, int MB>
 int32_t launch_smul_slots(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
     auto kern = k_scalar_mul_slots<T, MB>;
@@ -206,27 +240,27 @@ int32_t launch_smul_slots(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, siz
     CU(c, cudaGetLastError());
     return JJ_OK;
 }
-int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, size_t sc_stride, char* out,
-                    uint8_t* flag_out, size_t n, char** tbl, size_t* tbl_cap, bool scalar_mont,
-                    const PeerOut* peers = nullptr) {
-    int v = c->smul_variant > 0 && c->smul_variant < kNumVariants ? c->smul_variant : kDefaultVariant;
-    SmulArgs a{};
-    a.points = pts;
-    a.scalars = sc;
-    a.scalar_stride = sc_stride;
-    a.out = out;
-    a.flag_out = flag_out;
-    a.n = n;
-    a.scalar_mont = scalar_mont;
-    if (peers) a.peers = *peers;
+#endif
+// a.out_unit = 160: ExtendedPoint results.  64 / 32: the fused normalise epilogue (default mapping only); the caller
+// provides a.norm_scratch (norm_scratch_bytes()).
+size_t norm_scratch_bytes(const jj_ctx* c, size_t n) { return n * 128 + smul_round(c) * 32; }
+int32_t launch_smul(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
+    const SmulVariant& v = smul_variant(c);
+    if (a.out_unit != 160) {
+        if (v.id != kDefaultVariant) return fail(c, JJ_ERR_INVALID_ARG, "the fused normalise epilogue exists for the default mapping only");
+        return launch_smul_t<512, 1, TABLE_GMEM, true>(c, s, a, tbl, tbl_cap);
+    }
 #define V(ID, T, MB, TAB) \
-    case ID: return launch_smul_t<T, MB, TAB>(c, s, a, tbl, tbl_cap)
-    switch (v) {
+    case ID: return launch_smul_t<T, MB, TAB, false>(c, s, a, tbl, tbl_cap)
+    switch (v.id) {
+        V(13, 512, 1, TABLE_GMEM);
+        V(24, 768, 1, TABLE_GMEM);
+        V(5, 256, 1, TABLE_GMEM);
+#if defined(JJ_EXPERIMENTS)
         V(1, 224, 1, TABLE_SMEM);
         V(2, 128, 2, TABLE_GMEM);
         V(3, 128, 3, TABLE_GMEM);
         V(4, 128, 4, TABLE_GMEM);
-        V(5, 256, 1, TABLE_GMEM);
         V(6, 192, 1, TABLE_SMEM);
         V(7, 128, 1, TABLE_SMEM);
         V(8, 64, 3, TABLE_SMEM);
@@ -234,14 +268,12 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         V(10, 64, 6, TABLE_GMEM);
         V(11, 384, 1, TABLE_GMEM);
         V(12, 192, 2, TABLE_GMEM);
-        V(13, 512, 1, TABLE_GMEM);
         V(14, 320, 1, TABLE_GMEM);
         V(19, 448, 1, TABLE_GMEM);
         V(20, 480, 1, TABLE_GMEM);
         V(21, 256, 2, TABLE_GMEM);
         V(22, 576, 1, TABLE_GMEM);
         V(23, 640, 1, TABLE_GMEM);
-        V(24, 768, 1, TABLE_GMEM);
         V(25, 704, 1, TABLE_GMEM);
         V(26, 896, 1, TABLE_GMEM);
         V(27, 1024, 1, TABLE_GMEM);
@@ -249,9 +281,22 @@ int32_t launch_smul(jj_ctx* c, cudaStream_t s, const char* pts, const char* sc, 
         case 16: return launch_smul_slots<384, 1>(c, s, a, tbl, tbl_cap);
         case 17: return launch_smul_slots<544, 1>(c, s, a, tbl, tbl_cap);
         case 18: return launch_smul_slots<256, 2>(c, s, a, tbl, tbl_cap);
+#endif
     }
 #undef V
-    return fail(c, JJ_ERR_INVALID_ARG, "bad scalar-mul variant %d", v);
+    return fail(c, JJ_ERR_INVALID_ARG, "bad scalar-mul variant %d", v.id);
+}
+SmulArgs smul_args(const char* pts, bool in_affine, const char* sc, char* out, size_t n, bool scalar_mont) {
+    SmulArgs a{};
+    a.points = pts;
+    a.in_affine = in_affine;
+    a.scalars = sc;
+    a.scalar_stride = 32;
+    a.out = out;
+    a.n = n;
+    a.scalar_mont = scalar_mont;
+    a.out_unit = 160;
+    return a;
 }
 
 // ---- generic batched dispatch ---------------------------------------------------------------------
@@ -273,6 +318,8 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
         if (i.unit && !i.p && n) return fail(c, JJ_ERR_INVALID_ARG, "null input pointer");
     if (outs[0].unit && !outs[0].p && n) return fail(c, JJ_ERR_INVALID_ARG, "null output pointer");
     CU(c, cudaSetDevice(c->device));
+    if (capturing(c) && (flags & (JJ_DEVICE_PTRS | JJ_ASYNC)) != (JJ_DEVICE_PTRS | JJ_ASYNC))
+        return fail(c, JJ_ERR_INVALID_ARG, "only JJ_DEVICE_PTRS | JJ_ASYNC calls can be captured into a graph");
     if (n == 0) return JJ_OK;
     if (flags & JJ_DEVICE_PTRS) {
         const char* din[3];
@@ -301,7 +348,7 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
         size_t out_off[2] = {0, 0};
         for (int k = 0; k < 3; k++) {
             if (!ins[k].unit) continue;
-            int32_t rc = ensure(c, &S.buf[k], &S.cap[k], kChunkUnits * ins[k].unit);
+            int32_t rc = ensure(c, &S.buf[k], &S.cap[k], kChunkUnits * ins[k].unit, false);
             if (rc) return rc;
             CU(c, cudaMemcpyAsync(S.buf[k], (const char*)ins[k].p + done * ins[k].unit, cnt * ins[k].unit,
                                   cudaMemcpyHostToDevice, S.stream));
@@ -313,7 +360,7 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
                 out_off[k] = need;
                 need += (kChunkUnits * outs[k].unit + 255) & ~(size_t)255;
             }
-            int32_t rc = ensure(c, &S.buf[3], &S.cap[3], need);
+            int32_t rc = ensure(c, &S.buf[3], &S.cap[3], need, false);
             if (rc) return rc;
             for (int k = 0; k < 2; k++)
                 if (outs[k].unit && outs[k].p) dout[k] = S.buf[3] + out_off[k];
@@ -352,6 +399,14 @@ int32_t fe_binary(jj_ctx* c, const void* a, const void* b, void* out, size_t n, 
         return fe_launch<F, OP>(c, s, canon, din[0], din[1], dout[0], nullptr, cnt, 0, 0);
     });
 }
+// grid of the Montgomery-trick kernels: chains of `per_thread` elements per thread for large batches, in whole
+// multiples of `blocks_per_sm` x SM count blocks of 128 threads
+int chain_grid(const jj_ctx* c, size_t n, int per_thread, int blocks_per_sm) {
+    size_t blocks = (n + 128 * (size_t)per_thread - 1) / (128 * (size_t)per_thread);
+    size_t per_wave = (size_t)c->sm_count * blocks_per_sm;
+    blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
+    return (int)std::min(blocks, (n + 127) / 128);
+}
 // Batched inversion: chains of ~32 elements per thread share one Fermat inversion (k_fe_invert_batched).
 template <class F>
 int32_t fe_invert_batch(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t n, uint32_t flags) {
@@ -361,16 +416,13 @@ int32_t fe_invert_batch(jj_ctx* c, const void* a, void* out, uint8_t* ok, size_t
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
         char** scr = S ? &S->tmp2 : &c->tmp2;
         size_t* cap = S ? &S->tmp2_cap : &c->tmp2_cap;
-        int32_t rc = ensure(c, scr, cap, cnt * 32);
+        int32_t rc = ensure(c, scr, cap, cnt * 32, !S);
         if (rc) return rc;
-        size_t blocks = (cnt + 128 * 32 - 1) / (128 * 32);
-        size_t per_wave = (size_t)c->sm_count * 2;
-        blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
-        blocks = std::min(blocks, (cnt + 127) / 128);
+        const int blocks = chain_grid(c, cnt, 32, 2);
         if (canon)
-            k_fe_invert_batched<F, true><<<(int)blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], *scr, cnt);
+            k_fe_invert_batched<F, true><<<blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], *scr, cnt);
         else
-            k_fe_invert_batched<F, false><<<(int)blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], *scr, cnt);
+            k_fe_invert_batched<F, false><<<blocks, 128, 0, s>>>(din[0], dout[0], (uint8_t*)dout[1], *scr, cnt);
         c->launches++;
         CU(c, cudaGetLastError());
         return JJ_OK;
@@ -406,14 +458,20 @@ int32_t pt_binary(jj_ctx* c, const void* p, size_t pu, const void* q, size_t qu,
     });
 }
 
-int32_t normalize_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, size_t n) {
-    // one Fermat inversion per thread amortised over its strided chain: ~32 points per thread for
-    // large batches, grid sized in whole multiples of the SM count (2 x 128-thread blocks each)
-    size_t blocks = (n + 128 * 32 - 1) / (128 * 32);
-    size_t per_wave = (size_t)c->sm_count * 2;
-    blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
-    blocks = std::min(blocks, (n + 127) / 128);
-    k_batch_normalize<<<(int)blocks, 128, 0, s>>>(in, out, n);
+// ExtendedPoint (device) -> AffinePoint (fmt 64), encoding (fmt 32) or normalised ExtendedPoint (fmt 160, may be in
+// place).  One Fermat inversion per thread amortised over its strided chain (~32 points per thread for large batches).
+// fmt 32 / 160 need n x 32 B of scratch for the running products (fmt 64 keeps them in the output).
+int32_t normalize_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, size_t n, int fmt, char** scr, size_t* scr_cap,
+                         bool main_scratch) {
+    const int blocks = chain_grid(c, n, 32, 2);
+    if (fmt == 64) {
+        k_batch_normalize<64><<<blocks, 128, 0, s>>>(in, out, out, n);
+    } else {
+        int32_t rc = ensure(c, scr, scr_cap, n * 32, main_scratch);
+        if (rc) return rc;
+        if (fmt == 32) k_batch_normalize<32><<<blocks, 128, 0, s>>>(in, out, *scr, n);
+        else k_batch_normalize<160><<<blocks, 128, 0, s>>>(in, out, *scr, n);
+    }
     c->launches++;
     CU(c, cudaGetLastError());
     return JJ_OK;
@@ -421,11 +479,7 @@ int32_t normalize_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, s
 int32_t from_bytes_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, uint8_t* ok, size_t n, bool zip216) {
     // chains of ~8 encodings per thread: the Fermat inversion is amortised 8x while 4 x 128-thread blocks per
     // SM stay resident; grid in whole multiples of the SM count
-    size_t blocks = (n + 128 * 8 - 1) / (128 * 8);
-    size_t per_wave = (size_t)c->sm_count * 4;
-    blocks = std::max<size_t>(1, (blocks + per_wave - 1) / per_wave * per_wave);
-    blocks = std::min(blocks, (n + 127) / 128);
-    k_from_bytes<<<(int)blocks, 128, 0, s>>>(in, out, ok, n, zip216);
+    k_from_bytes<<<chain_grid(c, n, 8, 4), 128, 0, s>>>(in, out, ok, n, zip216);
     c->launches++;
     CU(c, cudaGetLastError());
     return JJ_OK;
@@ -436,24 +490,59 @@ int32_t to_bytes_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, si
     CU(c, cudaGetLastError());
     return JJ_OK;
 }
-// extended (device) -> requested output format (device)
-int32_t finish_output(jj_ctx* c, cudaStream_t s, const char* ext, char* out, size_t n, uint32_t flags, char** tmp2,
-                      size_t* tmp2_cap) {
-    if (flags & JJ_OUT_BYTES) {
-        int32_t rc = ensure(c, tmp2, tmp2_cap, n * 64);
-        if (rc) return rc;
-        rc = normalize_launch(c, s, ext, *tmp2, n);
-        if (rc) return rc;
-        return to_bytes_launch(c, s, *tmp2, out, n);
-    }
-    return normalize_launch(c, s, ext, out, n);
-}
 size_t out_unit(uint32_t flags) { return (flags & JJ_OUT_BYTES) ? 32 : (flags & JJ_OUT_AFFINE) ? 64 : 160; }
 
+// Variable-base scalar multiplication of `cnt` device-resident units into `dst` in the format the flags ask for.
+// ExtendedPoint output: one kernel.  AffinePoint / encoding output: either the kernel's fused normalise epilogue
+// (when every thread owns several units, i.e. device-resident batches of >= 4 rounds) or the kernel into an
+// ExtendedPoint scratch followed by one k_batch_normalize pass that writes the final format.
+int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in_affine, const char* sc, char* dst, size_t cnt,
+                 uint32_t flags, const PeerOut* peers = nullptr) {
+    char** tbl = S ? &S->tbl : &c->tbl;
+    size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
+    const int unit = (int)out_unit(flags);
+    SmulArgs a = smul_args(pts, in_affine, sc, dst, cnt, flags & JJ_SCALAR_MONT);
+    if (peers) a.peers = *peers;
+    if (unit == 160) return launch_smul(c, s, a, tbl, tcap);
+    const bool default_map = smul_variant(c).id == kDefaultVariant;
+    bool fused = !S && default_map && cnt >= 4 * smul_round(c);
+    if (c->smul_variant == kFusedNormOn) fused = !S;
+    if (c->smul_variant == kFusedNormOff) fused = false;
+    if (peers && peers->n_peers > 0) {
+        if (S || !default_map) return fail(c, JJ_ERR_INVALID_ARG, "fused gather of converted outputs needs the default mapping");
+        fused = true;
+    }
+    if (fused) {
+        int32_t rc = ensure(c, &c->norm, &c->norm_cap, norm_scratch_bytes(c, cnt));
+        if (rc) return rc;
+        a.out_unit = unit;
+        a.norm_scratch = c->norm;
+        return launch_smul(c, s, a, tbl, tcap);
+    }
+    // extended results go to scratch, then one pass normalises (and encodes) into the caller's buffer
+    char** tmp = S ? &S->buf[2] : &c->tmp;
+    size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;
+    int32_t rc = ensure(c, tmp, tmpcap, std::max(cnt, S ? kChunkUnits : cnt) * 160, !S);
+    if (rc) return rc;
+    a.out = *tmp;
+    rc = launch_smul(c, s, a, tbl, tcap);
+    if (rc) return rc;
+    // the running products of the normalise pass for 32-byte outputs live in the (dead) scalar-mul table scratch
+    return normalize_launch(c, s, *tmp, dst, cnt, unit, tbl, tcap, !S);
+}
+// whole rounds per staged chunk: a chunk that ends in a partly filled round leaves the multiplier pipe
+// under-occupied for that round
+size_t smul_chunk(const jj_ctx* c) {
+    const size_t round = smul_round(c);
+    return round && round <= kChunkUnits ? kChunkUnits / round * round : kChunkUnits;
+}
+
 // fixed-base window width: 7 (216 KB table, the default) or 4 (47 KB table, variant 100)
-int fixed_w(const jj_ctx* c) { return c->smul_variant == 100 ? 4 : 7; }
+int fixed_w(const jj_ctx* c) { return c->smul_variant == kFixedW4 ? 4 : 7; }
 
 int32_t build_fixed_table(jj_ctx* c, const void* base_affine, uint32_t flags) {
+    if (capturing(c))
+        return fail(c, JJ_ERR_INVALID_ARG, "jj_scalar_mul_fixed cannot be captured into a graph (the table cache is checked on the host)");
     char key[64];
     if (flags & JJ_DEVICE_PTRS)
         CU(c, cudaMemcpy(key, base_affine, 64, cudaMemcpyDeviceToHost));
@@ -494,6 +583,19 @@ int32_t launch_fixed(jj_ctx* c, cudaStream_t s, const char* scalars, char* dst, 
     return JJ_OK;
 }
 
+int32_t nccl_fail(jj_ctx* c, const char* what, int rc) {
+    return fail(c, JJ_ERR_NCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+}
+// 4-byte all-reduce on the context's stream: a stream-ordered rendezvous of all ranks
+int32_t rendezvous(jj_ctx* c) {
+    if (!c->barrier_word) {
+        CU(c, cudaMalloc((void**)&c->barrier_word, 256));
+        CU(c, cudaMemset(c->barrier_word, 0, 256));
+    }
+    int rc = g_nccl.AllReduce(c->barrier_word, c->barrier_word + 32, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+    return rc == 0 ? JJ_OK : nccl_fail(c, "ncclAllReduce", rc);
+}
+
 }  // namespace
 
 // =================================================================================== C ABI
@@ -516,14 +618,16 @@ int32_t jj_init(int device, jj_ctx** out) {
         delete c;
         return JJ_ERR_CUDA;
     }
-    if (prop.major < 10) {
+    if (prop.major != 10 || prop.minor != 0) {
         delete c;
-        return JJ_ERR_NO_DEVICE;  // sm_100a code only
+        return JJ_ERR_NO_DEVICE;  // the library holds sm_100a SASS only (no PTX): nothing else can run it
     }
     c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < kStages && ok; k++) ok = cudaStreamCreateWithFlags(&c->st[k].stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < kStages && ok; k++) ok = cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         jj_destroy(c);
         return JJ_ERR_CUDA;
@@ -568,11 +672,11 @@ int32_t jj_destroy(jj_ctx* c) {
         if (c->st[k].tmp2) cudaFree(c->st[k].tmp2);
         if (c->st[k].stream) cudaStreamDestroy(c->st[k].stream);
     }
-    for (void* p : {(void*)c->tbl, (void*)c->tmp, (void*)c->tmp2, (void*)c->fixed_table, (void*)c->fixed_base_dev,
-                    (void*)c->flush})
+    for (void* p : {(void*)c->tbl, (void*)c->tmp, (void*)c->tmp2, (void*)c->norm, (void*)c->fixed_table,
+                    (void*)c->fixed_base_dev, (void*)c->flush})
         if (p) cudaFree(p);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev_fork, c->ev_join[0], c->ev_join[1]})
+        if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return JJ_OK;
@@ -587,7 +691,10 @@ int32_t jj_sync(jj_ctx* c) {
 const char* jj_last_error(const jj_ctx* c) { return c ? c->err : "null context"; }
 uint64_t jj_launch_count(const jj_ctx* c) { return c ? c->launches : 0; }
 int32_t jj_set_scalar_mul_variant(jj_ctx* c, int32_t v) {
-    if (!c || v < 0 || (v >= kNumVariants && v != 100)) return JJ_ERR_INVALID_ARG;  // 100: fixed-base kernel with shared Fq bodies
+    if (!c) return JJ_ERR_INVALID_ARG;
+    bool known = v == 0 || v == kFixedW4 || v == kFusedNormOn || v == kFusedNormOff;
+    for (const SmulVariant& k : kVariants) known = known || k.id == v;
+    if (!known) return fail(c, JJ_ERR_INVALID_ARG, "unknown scalar-mul variant %d (experimental mappings need a -DJJ_EXPERIMENTS build)", v);
     c->smul_variant = v;
     return JJ_OK;
 }
@@ -672,6 +779,7 @@ int32_t jj_flush_l2(jj_ctx* c) {
 int32_t jj_graph_begin(jj_ctx* c) {
     if (!c) return JJ_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));
+    if (capturing(c)) return fail(c, JJ_ERR_INVALID_ARG, "a capture is already in progress");
     CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     return JJ_OK;
 }
@@ -684,6 +792,7 @@ int32_t jj_graph_end(jj_ctx* c, void** graph_exec) {
     cudaGraphDestroy(g);
     if (rc != cudaSuccess) return fail(c, JJ_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(rc));
     *graph_exec = e;
+    c->live_graphs++;  // scratch buffers stay where they are until the graph is destroyed (ensure())
     return JJ_OK;
 }
 int32_t jj_graph_launch(jj_ctx* c, void* graph_exec) {
@@ -696,12 +805,14 @@ int32_t jj_graph_launch(jj_ctx* c, void* graph_exec) {
 int32_t jj_graph_destroy(jj_ctx* c, void* graph_exec) {
     if (!c || !graph_exec) return JJ_ERR_INVALID_ARG;
     CU(c, cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    if (c->live_graphs > 0) c->live_graphs--;
     return JJ_OK;
 }
 
 int32_t jj_measure_imad_peak(jj_ctx* c, double* imad_per_sec) {
     if (!c || !imad_per_sec) return JJ_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));
+    if (capturing(c)) return fail(c, JJ_ERR_INVALID_ARG, "not capturable");
     int32_t rc = ensure(c, &c->tmp2, &c->tmp2_cap, 64);
     if (rc) return rc;
     const int iters = 20000, blocks = c->sm_count * 4;
@@ -831,64 +942,52 @@ int32_t jj_affine_to_niels(jj_ctx* c, const void* p, void* out, size_t n, uint32
     return pt_binary<PT_AFFINE_TO_NIELS>(c, p, 64, nullptr, 0, out, 96, n, flags);
 }
 
+int32_t jj_mul_by_cofactor(jj_ctx* c, const void* p, void* out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    In ins[3] = {{p, 160}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{out, 160}, {nullptr, 0}};
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
+        k_mul_by_cofactor<<<grid_for(c, cnt, 128, 4), 128, 0, s>>>(din[0], dout[0], cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
+    });
+}
+
 int32_t jj_scalar_mul(jj_ctx* c, const void* points, const void* scalars, void* out, size_t n, uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;
     if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
     In ins[3] = {{points, 160}, {scalars, 32}, {nullptr, 0}};
     Out outs[2] = {{out, out_unit(flags)}, {nullptr, 0}};
-    bool smont = flags & JJ_SCALAR_MONT, conv = flags & (JJ_OUT_AFFINE | JJ_OUT_BYTES);
-    // host batches are staged in chunks of whole "rounds" (one unit per resident thread): a chunk that ends in a
-    // partly filled round leaves the multiplier pipe under-occupied for that round
-    size_t chunk = kChunkUnits;
-    {
-        int v = c->smul_variant > 0 && c->smul_variant < kNumVariants ? c->smul_variant : kDefaultVariant;
-        size_t round = (size_t)c->sm_count * kVariants[v].threads * kVariants[v].min_blocks;
-        if (round && round <= kChunkUnits) chunk = kChunkUnits / round * round;
-    }
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
-        char** tbl = S ? &S->tbl : &c->tbl;
-        size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
-        if (!conv) return launch_smul(c, s, din[0], din[1], 32, dout[0], nullptr, cnt, tbl, tcap, smont);
-        // extended results go to scratch, then normalise (and encode) into the caller's buffer
-        char** tmp = S ? &S->buf[2] : &c->tmp;
-        size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;
-        int32_t rc = ensure(c, tmp, tmpcap, std::max(cnt, S ? kChunkUnits : cnt) * 160);
-        if (rc) return rc;
-        rc = launch_smul(c, s, din[0], din[1], 32, *tmp, nullptr, cnt, tbl, tcap, smont);
-        if (rc) return rc;
-        return finish_output(c, s, *tmp, dout[0], cnt, flags, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap);
-    }, chunk);
+        return smul_any(c, s, S, din[0], false, din[1], dout[0], cnt, flags);
+    }, smul_chunk(c));
 }
 
 int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scalars, void* out, uint8_t* ok, size_t n,
                               uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;
     if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    if ((flags & JJ_CHECK_SUBGROUP) && !ok && n) return fail(c, JJ_ERR_INVALID_ARG, "JJ_CHECK_SUBGROUP needs the ok[] array");
     In ins[3] = {{points32, 32}, {scalars, 32}, {nullptr, 0}};
     Out outs[2] = {{out, out_unit(flags)}, {ok, 1}};
-    const bool smont = flags & JJ_SCALAR_MONT, conv = flags & (JJ_OUT_AFFINE | JJ_OUT_BYTES), zip216 = !(flags & JJ_PRE_ZIP216);
+    const bool zip216 = !(flags & JJ_PRE_ZIP216), subgroup = flags & JJ_CHECK_SUBGROUP;
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
-        // decode -> affine scratch -> extended scratch -> scalar-mul (in place when the output is converted)
-        char** tbl = S ? &S->tbl : &c->tbl;
-        size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
-        char** ext = S ? &S->buf[2] : &c->tmp;
-        size_t* extcap = S ? &S->cap[2] : &c->tmp_cap;
+        // decode -> AffinePoint scratch (64 B) [-> subgroup test on it] -> scalar-mul reading the affine points directly
         char** aff = S ? &S->tmp2 : &c->tmp2;
         size_t* affcap = S ? &S->tmp2_cap : &c->tmp2_cap;
-        const size_t cap_units = std::max(cnt, S ? kChunkUnits : cnt);
-        int32_t rc = ensure(c, ext, extcap, cap_units * 160);
-        if (rc) return rc;
-        rc = ensure(c, aff, affcap, cap_units * 64);
+        int32_t rc = ensure(c, aff, affcap, std::max(cnt, S ? kChunkUnits : cnt) * 64, !S);
         if (rc) return rc;
         rc = from_bytes_launch(c, s, din[0], *aff, (uint8_t*)dout[1], cnt, zip216);
         if (rc) return rc;
-        k_affine_to_extended<<<grid_for(c, cnt, 256, 8), 256, 0, s>>>(*aff, *ext, cnt);
-        c->launches++;
-        CU(c, cudaGetLastError());
-        rc = launch_smul(c, s, *ext, din[1], 32, conv ? *ext : dout[0], nullptr, cnt, tbl, tcap, smont);
-        if (rc || !conv) return rc;
-        return finish_output(c, s, *ext, dout[0], cnt, flags, aff, affcap);
-    });
+        if (subgroup) {  // SubgroupPoint::from_bytes (src/lib.rs:1427-1429): decoded AND torsion free
+            k_is_torsion_free<64, false, true><<<grid_for(c, cnt, 128, 4), 128, 0, s>>>(*aff, (uint8_t*)dout[1], cnt);
+            c->launches++;
+            CU(c, cudaGetLastError());
+        }
+        return smul_any(c, s, S, *aff, true, din[1], dout[0], cnt, flags);
+    }, smul_chunk(c));
 }
 
 int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scalars, void* out, size_t n, uint32_t flags) {
@@ -900,21 +999,21 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
     if (rc0) return rc0;
     In ins[3] = {{scalars, 32}, {nullptr, 0}, {nullptr, 0}};
     Out outs[2] = {{out, out_unit(flags)}, {nullptr, 0}};
-    bool smont = flags & JJ_SCALAR_MONT, conv = flags & (JJ_OUT_AFFINE | JJ_OUT_BYTES);
+    const bool smont = flags & JJ_SCALAR_MONT;
+    const int unit = (int)out_unit(flags);
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
         char* dst = dout[0];
         char** tmp = S ? &S->buf[2] : &c->tmp;
         size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;
-        if (conv) {
-            int32_t rc = ensure(c, tmp, tmpcap, std::max(cnt, S ? kChunkUnits : cnt) * 160);
+        if (unit != 160) {
+            int32_t rc = ensure(c, tmp, tmpcap, std::max(cnt, S ? kChunkUnits : cnt) * 160, !S);
             if (rc) return rc;
             dst = *tmp;
         }
         int32_t rc = fixed_w(c) == 4 ? launch_fixed<256, 4, false>(c, s, din[0], dst, cnt, smont)
                                      : launch_fixed<512, 7, true>(c, s, din[0], dst, cnt, smont);
-        if (rc) return rc;
-        if (conv) return finish_output(c, s, dst, dout[0], cnt, flags, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap);
-        return JJ_OK;
+        if (rc || unit == 160) return rc;
+        return normalize_launch(c, s, dst, dout[0], cnt, unit, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap, !S);
     });
 }
 
@@ -923,8 +1022,16 @@ int32_t jj_batch_normalize(jj_ctx* c, const void* in, void* out, size_t n, uint3
     if (in == out && n) return fail(c, JJ_ERR_INVALID_ARG, "batch_normalize output must not alias its input");
     In ins[3] = {{in, 160}, {nullptr, 0}, {nullptr, 0}};
     Out outs[2] = {{out, 64}, {nullptr, 0}};
-    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) {
-        return normalize_launch(c, s, din[0], dout[0], cnt);
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) {
+        return normalize_launch(c, s, din[0], dout[0], cnt, 64, nullptr, nullptr, !S);
+    });
+}
+int32_t jj_batch_normalize_extended(jj_ctx* c, const void* in, void* out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    In ins[3] = {{in, 160}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{out, 160}, {nullptr, 0}};
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) {
+        return normalize_launch(c, s, din[0], dout[0], cnt, 160, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap, !S);
     });
 }
 int32_t jj_affine_to_bytes(jj_ctx* c, const void* in, void* out, size_t n, uint32_t flags) {
@@ -944,13 +1051,11 @@ int32_t jj_batch_from_bytes(jj_ctx* c, const void* in, void* out, uint8_t* ok, s
         return from_bytes_launch(c, s, din[0], dout[0], (uint8_t*)dout[1], cnt, zip216);
     });
 }
+}  // extern "C"
 
-int32_t jj_is_torsion_free(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n, uint32_t flags) {
-    if (!c) return JJ_ERR_INVALID_ARG;
-    if (!flags_out && n) return fail(c, JJ_ERR_INVALID_ARG, "null output pointer");
-    CU(c, cudaSetDevice(c->device));
-    // [r]P == identity with r = FR_MODULUS_BYTES (src/lib.rs:73-76, 709-711); r is the same for every unit, so
-    // the batch shares its width-5 NAF (42 additions instead of the 58 of the per-unit signed radix-16 windows)
+// [r]P == identity by the reference's own route (src/lib.rs:709-711): the batch shares r, so its width-5 NAF (42
+// additions instead of the 58 of the per-unit signed radix-16 windows) drives one scalar-mul kernel.  JJ_TORSION_LADDER.
+static int32_t torsion_ladder(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n, uint32_t flags) {
     static const NafDigits naf = [] {
         const uint32_t r_words[8] = {FrP::M0, FrP::M1, FrP::M2, FrP::M3, FrP::M4, FrP::M5, FrP::M6, FrP::M7};
         NafDigits d;
@@ -964,7 +1069,7 @@ int32_t jj_is_torsion_free(jj_ctx* c, const void* p, uint8_t* flags_out, size_t 
         size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
         constexpr int T = 512;
         int grid = grid_for(c, cnt, T, 1);
-        int32_t rc = ensure(c, tbl, tcap, (size_t)grid * (T / 32) * 32768);
+        int32_t rc = ensure(c, tbl, tcap, (size_t)grid * (T / 32) * 32768, !S);
         if (rc) return rc;
         SmulArgs a{};
         a.points = din[0];
@@ -977,7 +1082,18 @@ int32_t jj_is_torsion_free(jj_ctx* c, const void* p, uint8_t* flags_out, size_t 
         return JJ_OK;
     });
 }
-}  // extern "C"
+// Subgroup tests by the order-8 Tate pairing (torsion.cuh): one 223-bit power instead of a scalar multiplication.
+template <bool PRIME_ORDER>
+static int32_t torsion_pairing(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n, uint32_t flags) {
+    In ins[3] = {{p, 160}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{flags_out, 1}, {nullptr, 0}};
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
+        k_is_torsion_free<160, PRIME_ORDER, false><<<grid_for(c, cnt, 128, 4), 128, 0, s>>>(din[0], (uint8_t*)dout[0], cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
+    });
+}
 template <int WHAT>
 static int32_t point_flag(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n, uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;
@@ -992,7 +1108,19 @@ static int32_t point_flag(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n
     });
 }
 
-extern "C" {int32_t jj_is_identity(jj_ctx* c, const void* p, uint8_t* f, size_t n, uint32_t flags) { return point_flag<0>(c, p, f, n, flags); }
+extern "C" {
+int32_t jj_is_torsion_free(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (!flags_out && n) return fail(c, JJ_ERR_INVALID_ARG, "null output pointer");
+    if (flags & JJ_TORSION_LADDER) return torsion_ladder(c, p, flags_out, n, flags);
+    return torsion_pairing<false>(c, p, flags_out, n, flags);
+}
+int32_t jj_is_prime_order(jj_ctx* c, const void* p, uint8_t* flags_out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (!flags_out && n) return fail(c, JJ_ERR_INVALID_ARG, "null output pointer");
+    return torsion_pairing<true>(c, p, flags_out, n, flags);
+}
+int32_t jj_is_identity(jj_ctx* c, const void* p, uint8_t* f, size_t n, uint32_t flags) { return point_flag<0>(c, p, f, n, flags); }
 int32_t jj_is_small_order(jj_ctx* c, const void* p, uint8_t* f, size_t n, uint32_t flags) { return point_flag<1>(c, p, f, n, flags); }
 
 // ---- multi-GPU -----------------------------------------------------------------------------------------
@@ -1003,12 +1131,12 @@ int32_t jj_comm_unique_id(void* id128) {
 }
 int32_t jj_comm_init(jj_ctx* c, int32_t nranks, int32_t rank, const void* id128) {
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return JJ_ERR_INVALID_ARG;
-    if (!load_nccl()) return fail(c, JJ_ERR_NCCL, "libnccl.so.2 not found");
+    if (!load_nccl()) return fail(c, JJ_ERR_NCCL, "libnccl.so.2 not found (or it lacks an entry point this library calls)");
     CU(c, cudaSetDevice(c->device));
     Id128 id;
     memcpy(id.b, id128, 128);
     int rc = g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank);
-    if (rc != 0) return fail(c, JJ_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    if (rc != 0) return nccl_fail(c, "ncclCommInitRank", rc);
     c->nranks = nranks;
     c->rank = rank;
     return JJ_OK;
@@ -1019,46 +1147,126 @@ int32_t jj_comm_destroy(jj_ctx* c) {
     c->nccl_comm = nullptr;
     c->nranks = 1;
     c->rank = 0;
+    c->peers.n_peers = 0;
+    return JJ_OK;
+}
+}  // extern "C"
+
+// Block partition of SURVEY.md section 8e: rank g of G owns [g*n/G, (g+1)*n/G) -- blocks differ by at most one unit.
+static size_t shard_begin(size_t n_total, int rank, int nranks) { return (size_t)((unsigned __int128)n_total * rank / nranks); }
+
+// All ranks' blocks of out_all <- every rank's own block (already in place).  Equal blocks: one in-place
+// ncclAllGather; ragged blocks: one ncclBroadcast per rank inside a group (the usual all-gather-v).
+static int32_t gather_blocks(jj_ctx* c, char* out_all, size_t n_total, size_t unit) {
+    if (c->nranks == 1) return JJ_OK;
+    if (!c->nccl_comm) return fail(c, JJ_ERR_NCCL, "jj_comm_init was not called");
+    if (n_total % c->nranks == 0) {
+        const size_t blk = n_total / c->nranks * unit;
+        int rc = g_nccl.AllGather(out_all + (size_t)c->rank * blk, out_all, blk, /*ncclInt8*/ 0, c->nccl_comm, c->stream);
+        return rc == 0 ? JJ_OK : nccl_fail(c, "ncclAllGather", rc);
+    }
+    int rc = g_nccl.GroupStart();
+    for (int r = 0; r < c->nranks && rc == 0; r++) {
+        const size_t lo = shard_begin(n_total, r, c->nranks), hi = shard_begin(n_total, r + 1, c->nranks);
+        char* blk = out_all + lo * unit;
+        if (hi > lo) rc = g_nccl.Broadcast(blk, blk, (hi - lo) * unit, /*ncclInt8*/ 0, r, c->nccl_comm, c->stream);
+    }
+    int rc2 = g_nccl.GroupEnd();
+    if (rc != 0 || rc2 != 0) return nccl_fail(c, "ncclBroadcast group", rc ? rc : rc2);
+    return JJ_OK;
+}
+
+extern "C" {
+int32_t jj_scalar_mul_sharded_n(jj_ctx* c, const void* points_local, const void* scalars_local, void* out_all,
+                                void* out_local_host, size_t n_total, uint32_t flags) {
+    if (!c || !out_all) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    CU(c, cudaSetDevice(c->device));
+    if (capturing(c)) return fail(c, JJ_ERR_INVALID_ARG, "jj_scalar_mul_sharded cannot be captured into a graph");
+    const size_t unit = out_unit(flags);
+    const size_t lo = shard_begin(n_total, c->rank, c->nranks), n_local = shard_begin(n_total, c->rank + 1, c->nranks) - lo;
+    const bool host_in = !(flags & JJ_DEVICE_PTRS);
+    if (n_local && (!points_local || !scalars_local)) return fail(c, JJ_ERR_INVALID_ARG, "null input pointer");
+    if ((uintptr_t)out_all & 31) return fail(c, JJ_ERR_INVALID_ARG, "device pointer not 32-byte aligned");
+    if (!host_in && (((uintptr_t)points_local | (uintptr_t)scalars_local) & 31))
+        return fail(c, JJ_ERR_INVALID_ARG, "device pointer not 32-byte aligned");
+    if (c->nranks > 1 && !c->nccl_comm) return fail(c, JJ_ERR_NCCL, "jj_comm_init was not called");
+    // (host-staged chunks with converted outputs go through the ExtendedPoint scratch + normalise pass of one rank:
+    // they use the NCCL gather)
+    const bool fused = c->peers.n_peers == c->nranks && c->nranks > 1 && !(host_in && unit != 160);
+    if (fused && c->peers.ptr[c->rank] != (char*)out_all) return fail(c, JJ_ERR_INVALID_ARG, "out_all is not the registered peer buffer");
+    PeerOut po = c->peers;
+    po.base_unit = lo;
+    if (fused) {
+        // Leading rendezvous: a peer may still be reading the previous contents of ITS copy of out_all (work it
+        // ordered on its context's stream, or finished on the host, before entering this call); nobody stores into
+        // anybody's buffer before every rank has arrived here.
+        int32_t rc = rendezvous(c);
+        if (rc) return rc;
+    }
+    char* mine = (char*)out_all + lo * unit;
+    if (!host_in) {
+        int32_t rc = JJ_OK;
+        if (n_local)
+            rc = smul_any(c, c->stream, nullptr, (const char*)points_local, false, (const char*)scalars_local,
+                          fused ? nullptr : mine, n_local, flags, fused ? &po : nullptr);
+        if (rc) return rc;
+        if (out_local_host && n_local)
+            CU(c, cudaMemcpyAsync(out_local_host, mine, n_local * unit, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        // host inputs: this rank's block is staged in round-sized chunks on the two staging streams (upload of chunk
+        // k+1 overlaps the kernel of chunk k); every chunk's kernel writes its results into place -- all ranks' buffers
+        // when fused -- and the chunk is read back to the host from this rank's own copy.
+        CU(c, cudaEventRecord(c->ev_fork, c->stream));
+        const size_t chunk = smul_chunk(c);
+        size_t done = 0;
+        int stage = 0, used = 0;
+        while (done < n_local) {
+            const size_t cnt = std::min(chunk, n_local - done);
+            Staging& S = c->st[stage];
+            CU(c, cudaStreamSynchronize(S.stream));
+            if (used < kStages) {
+                CU(c, cudaStreamWaitEvent(S.stream, c->ev_fork, 0));
+                used++;
+            }
+            int32_t rc = ensure(c, &S.buf[0], &S.cap[0], kChunkUnits * 160, false);
+            if (!rc) rc = ensure(c, &S.buf[1], &S.cap[1], kChunkUnits * 32, false);
+            if (rc) return rc;
+            CU(c, cudaMemcpyAsync(S.buf[0], (const char*)points_local + done * 160, cnt * 160, cudaMemcpyHostToDevice, S.stream));
+            CU(c, cudaMemcpyAsync(S.buf[1], (const char*)scalars_local + done * 32, cnt * 32, cudaMemcpyHostToDevice, S.stream));
+            PeerOut pc = po;
+            pc.base_unit = lo + done;
+            rc = smul_any(c, S.stream, &S, S.buf[0], false, S.buf[1], fused ? nullptr : mine + done * unit, cnt, flags,
+                          fused ? &pc : nullptr);
+            if (rc) return rc;
+            if (out_local_host)
+                CU(c, cudaMemcpyAsync((char*)out_local_host + done * unit, mine + done * unit, cnt * unit,
+                                      cudaMemcpyDeviceToHost, S.stream));
+            done += cnt;
+            stage = (stage + 1) % kStages;
+        }
+        for (int k = 0; k < used; k++) {  // join: the main stream continues after every chunk
+            CU(c, cudaEventRecord(c->ev_join[k], c->st[k].stream));
+            CU(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+        }
+    }
+    if (fused) {
+        // Trailing rendezvous: once this 4-byte all-reduce completes here, every peer's kernel (enqueued before its
+        // own all-reduce) has finished storing into this rank's buffer.
+        int32_t rc = rendezvous(c);
+        if (rc) return rc;
+    } else {
+        int32_t rc = gather_blocks(c, (char*)out_all, n_total, unit);
+        if (rc) return rc;
+    }
+    if (!(flags & JJ_ASYNC) || host_in) CU(c, cudaStreamSynchronize(c->stream));
     return JJ_OK;
 }
 int32_t jj_scalar_mul_sharded(jj_ctx* c, const void* points_local, const void* scalars_local, void* out_all,
                               size_t n_local, uint32_t flags) {
-    if (!c || !out_all) return JJ_ERR_INVALID_ARG;
+    if (!c) return JJ_ERR_INVALID_ARG;
     if (!(flags & JJ_DEVICE_PTRS)) return fail(c, JJ_ERR_INVALID_ARG, "jj_scalar_mul_sharded takes device pointers");
-    CU(c, cudaSetDevice(c->device));
-    size_t unit = out_unit(flags);
-    bool fused = c->peers.n_peers == c->nranks && c->nranks > 1 && unit == 160;
-    if (fused) {
-        // compute + all-gather in ONE kernel: results are stored into every rank's gathered buffer
-        if (c->peers.ptr[c->rank] != (char*)out_all) return fail(c, JJ_ERR_INVALID_ARG, "out_all is not the registered peer buffer");
-        if (((uintptr_t)points_local | (uintptr_t)scalars_local | (uintptr_t)out_all) & 31)
-            return fail(c, JJ_ERR_INVALID_ARG, "device pointer not 32-byte aligned");
-        PeerOut po = c->peers;
-        po.base_unit = (size_t)c->rank * n_local;
-        int32_t rc = launch_smul(c, c->stream, (const char*)points_local, (const char*)scalars_local, 32, nullptr, nullptr,
-                                 n_local, &c->tbl, &c->tbl_cap, flags & JJ_SCALAR_MONT, &po);
-        if (rc) return rc;
-        // stream-ordered rendezvous: once this 4-byte all-reduce completes here, every peer's kernel
-        // (enqueued before its own all-reduce) has finished storing into this rank's buffer
-        if (!c->barrier_word) {
-            CU(c, cudaMalloc((void**)&c->barrier_word, 256));
-            CU(c, cudaMemset(c->barrier_word, 0, 256));
-        }
-        int nrc = g_nccl.AllReduce(c->barrier_word, c->barrier_word + 32, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->nccl_comm, c->stream);
-        if (nrc != 0) return fail(c, JJ_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
-    } else {
-        char* mine = (char*)out_all + (size_t)c->rank * n_local * unit;
-        int32_t rc = jj_scalar_mul(c, points_local, scalars_local, mine, n_local, flags | JJ_ASYNC);
-        if (rc) return rc;
-        if (c->nranks > 1) {
-            if (!c->nccl_comm) return fail(c, JJ_ERR_NCCL, "jj_comm_init was not called");
-            // in-place all-gather: every rank's block already sits at its own offset
-            int nrc = g_nccl.AllGather(mine, out_all, n_local * unit, /*ncclInt8*/ 0, c->nccl_comm, c->stream);
-            if (nrc != 0) return fail(c, JJ_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
-        }
-    }
-    if (!(flags & JJ_ASYNC)) CU(c, cudaStreamSynchronize(c->stream));
-    return JJ_OK;
+    return jj_scalar_mul_sharded_n(c, points_local, scalars_local, out_all, nullptr, n_local * (size_t)c->nranks, flags);
 }
 
 int32_t jj_ipc_export(jj_ctx* c, const void* dptr, void* handle64) {

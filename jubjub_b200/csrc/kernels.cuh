@@ -9,7 +9,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "slotmul.cuh"
+#include "scalarmul.cuh"
+#include "torsion.cuh"
+#if defined(JJ_EXPERIMENTS)
+#include "slotmul.cuh"  // shared-memory slot-file mapping (measured slower): not in the default build
+#endif
 
 namespace jj {
 
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(128) k_point_op(const char* __restrict__ p, co
     }
 }
 
-// flags: 0 is_identity, 1 is_small_order
+// flags: 0 is_identity (src/lib.rs:691-696), 1 is_small_order (:699-705)
 template <int WHAT>
 __global__ void __launch_bounds__(128) k_point_flag(const char* __restrict__ p, uint8_t* __restrict__ out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -283,11 +287,44 @@ __global__ void __launch_bounds__(128) k_point_flag(const char* __restrict__ p, 
         }
     }
 }
+// mul_by_cofactor (src/lib.rs:722-724): three doublings with the reference's formula sequence => all 160 bytes equal.
+__global__ void __launch_bounds__(128) k_mul_by_cofactor(const char* __restrict__ p, char* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ext_point P;
+        ld_ext(P, p, i);
+        point_double_t<true>(P, P);
+        point_double_t<true>(P, P);
+        point_double_t<true>(P, P);
+        st_ext(out, i, P);
+    }
+}
+// Subgroup membership by the order-8 Tate pairing (torsion.cuh) -- is_torsion_free (src/lib.rs:709-711) and,
+// with PRIME_ORDER, is_prime_order (:717-719: torsion free and not the identity).  STRIDE is the byte size of one
+// input point: 160 (ExtendedPoint) or 64 (AffinePoint, z = 1).  With AND_INTO the result is combined with the flag
+// already in out[i] (the `ok` of a preceding decode: SubgroupPoint::from_bytes, src/lib.rs:1427-1429).
+template <int STRIDE, bool PRIME_ORDER, bool AND_INTO>
+__global__ void __launch_bounds__(128, 4) k_is_torsion_free(const char* __restrict__ p, uint8_t* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fe U, V, Z;
+        ld_fe(U, p + i * STRIDE);
+        ld_fe(V, p + i * STRIDE + 32);
+        if (STRIDE == 160) ld_fe(Z, p + i * STRIDE + 64);
+        else fe_set_one<FqP>(Z);
+        bool f = point_is_torsion_free(U, V, Z);
+        if (PRIME_ORDER) f = f && !(fe_is_zero(U) && fe_eq(V, Z));
+        if (AND_INTO) f = f && out[i] != 0;
+        out[i] = f ? 1 : 0;
+    }
+}
 
 // ---- variable-base scalar multiplication -------------------------------------------------------
+#if defined(JJ_EXPERIMENTS)
 // Window table in shared memory: one 32 KB slab per warp, laid out [entry][fe][half][lane] in
 // 16-byte units, so a lane reading *its own* entry index is bank-conflict free (every quarter-
 // warp touches eight distinct 16-byte bank groups regardless of the entry each lane picks).
+// Measured slower than the L2-resident table (occupancy capped at 7 warps/SM): experiments only.
 struct SmemTable {
     uint4* slab;  // warp slab + lane
     __device__ __forceinline__ void put(int idx, const fe& f) {
@@ -306,6 +343,7 @@ struct SmemTable {
         get(j * 4, n.vpu); get(j * 4 + 1, n.vmu); get(j * 4 + 2, n.z); get(j * 4 + 3, n.t2d);
     }
 };
+#endif
 // Window table in global scratch (L2-resident: resident threads x 1 KB), laid out
 // [warp][entry][fe][lane][8 words]: table build stores are fully coalesced 256-bit stores,
 // lookups read four whole 32-byte sectors.
@@ -340,8 +378,21 @@ struct SmulArgs {
     size_t n;
     char* tbl_scratch;
     bool scalar_mont;
+    bool in_affine;      // points are AffinePoint (64 B): (u, v) -> (u, v, 1, u, v), src/lib.rs:214-226
+    int out_unit;        // NORM kernels: 64 = AffinePoint, 32 = encoding (src/lib.rs:455-464)
+    char* norm_scratch;  // NORM kernels: n x 128 B (u, v, z, prefix product) + one 32 B running product per thread
     PeerOut peers;
 };
+__device__ __forceinline__ void ld_point_any(ext_point& P, const SmulArgs& a, size_t i) {
+    if (a.in_affine) {
+        aff_point q;
+        ld_fe_stream(q.u, a.points + i * 64);
+        ld_fe_stream(q.v, a.points + i * 64 + 32);
+        point_from_affine(P, q);
+    } else {
+        ld_ext_stream(P, a.points, i);
+    }
+}
 __device__ __forceinline__ void smul_store(const SmulArgs& a, size_t i, const ext_point& acc) {
     if (a.peers.n_peers > 0) {
 #pragma unroll 1
@@ -350,38 +401,118 @@ __device__ __forceinline__ void smul_store(const SmulArgs& a, size_t i, const ex
         st_ext_stream(a.out, i, acc);
     }
 }
+// normalised result -> AffinePoint (64 B) or its encoding (32 B), into `out` or into every peer's gathered buffer
+__device__ __forceinline__ void smul_store_norm(const SmulArgs& a, size_t i, const fe& x, const fe& y) {
+    fe enc;
+    if (a.out_unit == 32) {  // AffinePoint::to_bytes: canonical v, bit 255 = parity of canonical u
+        fe xc;
+        fe_to_canonical<FqP>(xc, x);
+        fe_to_canonical<FqP>(enc, y);
+        enc.w[7] |= (xc.w[0] & 1u) << 31;
+    }
+    const int np = a.peers.n_peers > 0 ? a.peers.n_peers : 1;
+#pragma unroll 1
+    for (int r = 0; r < np; r++) {
+        char* base = a.peers.n_peers > 0 ? a.peers.ptr[r] : a.out;
+        const size_t u = a.peers.n_peers > 0 ? a.peers.base_unit + i : i;
+        if (a.out_unit == 32) {
+            st_fe_stream(base + u * 32, enc);
+        } else {
+            st_fe_stream(base + u * 64, x);
+            st_fe_stream(base + u * 64 + 32, y);
+        }
+    }
+}
 
-template <int THREADS, int MIN_BLOCKS, int TABLE>
+// NORM = false: results leave as ExtendedPoint (160 B).  NORM = true: batch_normalize (src/lib.rs:1084-1107) and, for
+// out_unit = 32, AffinePoint::to_bytes (:455-464) are folded into the kernel -- every thread keeps (u, v, z, prefix
+// product of its earlier z) of its own units in scratch, inverts the product of all its z once (Montgomery's trick along
+// the thread's own units, as ff::BatchInverter does along the slice; z = 0 is skipped and yields (0, 0)) and walks back.
+// The fused all-gather then moves 32-byte encodings instead of 160-byte points.  Worth it when a thread owns several
+// units (device-resident batches); host-staged chunks of one round use the separate k_batch_normalize pass.
+template <int THREADS, int MIN_BLOCKS, int TABLE, bool NORM>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulArgs a) {
+#if defined(JJ_EXPERIMENTS)
     extern __shared__ uint4 smem_tbl[];
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t stride = (size_t)gridDim.x * THREADS;
     // warp-major slot order: warp w of every block comes before warp w+1 of any block, so the last,
     // partial round of the batch leaves every SM with the same number of busy warps instead of
     // leaving whole SMs idle (the kernel is pipe-bound: fewer warps per SM finish proportionally sooner)
     const size_t slot = ((size_t)warp * gridDim.x + blockIdx.x) * 32 + lane;
+    char* run_slot = NORM ? a.norm_scratch + a.n * 128 + slot * 32 : nullptr;
+    if (NORM && slot < a.n) {
+        fe one;
+        fe_set_one<FqP>(one);
+        st_fe(run_slot, one);
+    }
     for (size_t i = slot; i < a.n; i += stride) {
         ext_point P, acc;
         fe k;
-        ld_ext_stream(P, a.points, i);
+        ld_point_any(P, a, i);
         ld_fe_stream(k, a.scalars + i * a.scalar_stride);
         if (a.scalar_mont) fe_to_canonical<FrP>(k, k);  // Fr::to_bytes, src/lib.rs:877
+#if defined(JJ_EXPERIMENTS)
         if (TABLE == TABLE_SMEM) {
             SmemTable t{smem_tbl + (size_t)warp * 2048 + lane};
             scalar_mul_core(acc, P, k.w, t);
-        } else {
+        } else
+#endif
+        {
             size_t gwarp = (size_t)blockIdx.x * (THREADS / 32) + warp;
             GmemTable t{a.tbl_scratch + gwarp * 32768 + lane * 32};
             scalar_mul_core(acc, P, k.w, t);
         }
-        if (a.flag_out) a.flag_out[i] = point_is_identity(acc) ? 1 : 0;  // is_torsion_free
-        else smul_store(a, i, acc);
+        if (NORM) {
+            fe run;
+            char* rec = a.norm_scratch + i * 128;
+            ld_fe(run, run_slot);
+            st_fe_stream(rec, acc.u);
+            st_fe_stream(rec + 32, acc.v);
+            st_fe_stream(rec + 64, acc.z);
+            st_fe_stream(rec + 96, run);
+            if (!fe_is_zero(acc.z)) {
+                fq_mul(run, run, acc.z);
+                st_fe(run_slot, run);
+            }
+        } else if (a.flag_out) {
+            a.flag_out[i] = point_is_identity(acc) ? 1 : 0;
+        } else {
+            smul_store(a, i, acc);
+        }
+    }
+    if (NORM && slot < a.n) {
+        fe inv;
+        ld_fe(inv, run_slot);
+        fq_pow_const_shared<ExpInvert<FqP>>(inv, inv);
+        const size_t cnt = (a.n - slot + stride - 1) / stride;
+#pragma unroll 1
+        for (size_t c = cnt; c-- > 0;) {
+            const size_t i = slot + c * stride;
+            const char* rec = a.norm_scratch + i * 128;
+            fe u, v, z, pre, zi;
+            ld_fe_stream(u, rec);
+            ld_fe_stream(v, rec + 32);
+            ld_fe_stream(z, rec + 64);
+            ld_fe_stream(pre, rec + 96);
+            if (fe_is_zero(z)) {
+                fe_set_zero(zi);
+            } else {
+                fq_mul(zi, pre, inv);
+                fq_mul(inv, inv, z);
+            }
+            fq_mul(u, u, zi);
+            fq_mul(v, v, zi);
+            smul_store_norm(a, i, u, v);
+        }
     }
 }
 
-// One scalar for the whole batch, given as its width-5 NAF (scalarmul.cuh): is_torsion_free with k = r
-// (src/lib.rs:709-711).  Same mapping and table scratch as k_scalar_mul; digits come from the kernel
-// parameters (uniform loads), so the add / no-add branch is warp-uniform.
+// One scalar for the whole batch, given as its width-5 NAF (scalarmul.cuh).  This is the reference's own
+// is_torsion_free, [r]P == O (src/lib.rs:709-711), kept as the on-device cross-check of the pairing test
+// (jj_is_torsion_free with JJ_TORSION_LADDER).  Same mapping and table scratch as k_scalar_mul; digits come
+// from the kernel parameters (uniform loads), so the add / no-add branch is warp-uniform.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_scalar_mul_const(const SmulArgs a, const NafDigits naf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -398,6 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_scalar_mul_const(const SmulArgs 
     }
 }
 
+#if defined(JJ_EXPERIMENTS)
 // Slot-file mapping (slotmul.cuh): the working set of each thread lives in 13 shared-memory slots
 // (13 KB per warp), field operations are shared noinline routines.  Window table in global scratch.
 template <int THREADS, int MIN_BLOCKS>
@@ -425,6 +557,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul_slots(const 
         else smul_store(a, i, acc);
     }
 }
+#endif
 
 // ---- fixed-base scalar multiplication -----------------------------------------------------------
 // Builds entry e of the fixed-base table (scalarmul.cuh): thread e runs the variable-base core on
@@ -532,17 +665,22 @@ __global__ void __launch_bounds__(THREADS)
 
 // ---- normalisation / encoding -------------------------------------------------------------------
 // batch_normalize (src/lib.rs:840-858, 1084-1107): Montgomery's trick along each thread's strided
-// chain (elements t, t+T, t+2T, ...), one Fermat inversion per thread.  out[i].u doubles as the
-// running-product scratch, as the reference uses q.u / q.v.  z == 0 is skipped and yields (0, 0).
-__global__ void __launch_bounds__(128) k_batch_normalize(const char* __restrict__ in, char* __restrict__ out, size_t n) {
+// chain (elements t, t+T, t+2T, ...), one Fermat inversion per thread.  `scratch` (n x 32 B; for FMT = 64 it is
+// out[i].u itself, as the reference uses q.u / q.v) holds the running products.  z == 0 is skipped and yields (0, 0).
+// FMT: 64 = AffinePoint out (the iterator form, :840-858); 32 = the encoding of that point (AffinePoint::to_bytes fused,
+// :455-464); 160 = the reference's in-place form (:1084-1107): the ExtendedPoint itself becomes (u/z, v/z, 1, u/z, v/z)
+// and `out` may be `in`.
+template <int FMT>
+__global__ void __launch_bounds__(128) k_batch_normalize(const char* in, char* out, char* scratch, size_t n) {
     const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    const size_t sstride = FMT == 64 ? 64 : 32;
     fe acc, z;
     fe_set_one<FqP>(acc);
     size_t cnt = 0;
     for (size_t i = t; i < n; i += T, cnt++) {
         ld_fe(z, in + i * 160 + 64);
-        st_fe(out + i * 64, acc);
+        st_fe(scratch + i * sstride, acc);
         if (!fe_is_zero(z)) mont_mul<FqP>(acc, acc, z);
     }
     fe_invert<FqP>(acc, acc);
@@ -552,7 +690,7 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const char* __restrict_
         ld_fe(z, in + i * 160 + 64);
         ld_fe(u, in + i * 160);
         ld_fe(v, in + i * 160 + 32);
-        ld_fe(s, out + i * 64);
+        ld_fe(s, scratch + i * sstride);
         if (fe_is_zero(z)) {
             fe_set_zero(zi);
         } else {
@@ -561,8 +699,25 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const char* __restrict_
         }
         mont_mul<FqP>(u, u, zi);
         mont_mul<FqP>(v, v, zi);
-        st_fe(out + i * 64, u);
-        st_fe(out + i * 64 + 32, v);
+        if (FMT == 64) {
+            st_fe(out + i * 64, u);
+            st_fe(out + i * 64 + 32, v);
+        } else if (FMT == 32) {
+            fe uc;
+            fe_to_canonical<FqP>(uc, u);
+            fe_to_canonical<FqP>(v, v);
+            v.w[7] |= (uc.w[0] & 1u) << 31;
+            st_fe(out + i * 32, v);
+        } else {
+            // the reference's loop sets z = one for every point; a skipped z = 0 therefore ends as (0, 0, 1, 0, 0)
+            fe one;
+            fe_set_one<FqP>(one);
+            st_fe(out + i * 160, u);
+            st_fe(out + i * 160 + 32, v);
+            st_fe(out + i * 160 + 64, one);
+            st_fe(out + i * 160 + 96, u);
+            st_fe(out + i * 160 + 128, v);
+        }
     }
 }
 // AffinePoint::to_bytes (src/lib.rs:455-464): canonical v, bit 255 = lsb of canonical u.
@@ -637,20 +792,6 @@ __global__ void __launch_bounds__(128, 4) k_from_bytes(const char* __restrict__ 
         st_fe(out + i * 64, p.u);
         st_fe(out + i * 64 + 32, p.v);
         if (ok) ok[i] = good ? 1 : 0;
-    }
-}
-
-// AffinePoint -> ExtendedPoint (src/lib.rs:214-226): (u, v, 1, u, v).  Used between the decode and the scalar-mul
-// kernels of jj_scalar_mul_encoded.
-__global__ void __launch_bounds__(256) k_affine_to_extended(const char* __restrict__ in, char* __restrict__ out, size_t n) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        aff_point a;
-        ext_point p;
-        ld_fe(a.u, in + i * 64);
-        ld_fe(a.v, in + i * 64 + 32);
-        point_from_affine(p, a);
-        st_ext(out, i, p);
     }
 }
 

@@ -66,6 +66,7 @@ class Engine:
         if rc != 0:
             raise JubjubError(rc, f"jj_init(device={device}) failed -- a B200 (sm_100) device is required")
         self.ctx, self.device = ctx, device
+        self.nranks, self.rank = 1, 0
 
     def close(self):
         if self.ctx:
@@ -98,6 +99,11 @@ class Engine:
         if out is not None:
             if isinstance(out, DeviceArray) != like_device:
                 raise ValueError("inputs and output must all be host arrays or all DeviceArrays")
+            # the kernel (or the D2H copy) writes n x width elements: a smaller or differently typed buffer is overrun
+            if out.dtype != np.dtype(dtype) or len(out.shape) != 2 or out.shape[1] != width or out.shape[0] < n:
+                raise ValueError(f"out must be ({n}, {width}) {np.dtype(dtype)} (more rows allowed), got {out.shape} {out.dtype}")
+            if not like_device and not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be C-contiguous")
             return out
         return DeviceArray(self, (n, width), dtype) if like_device else np.empty((n, width), dtype=dtype)
 
@@ -200,23 +206,28 @@ class Engine:
         return {"extended": (EXT_W, np.uint64, 0), "affine": (AFF_W, np.uint64, L.JJ_OUT_AFFINE),
                 "bytes": (32, np.uint8, L.JJ_OUT_BYTES)}[output]
 
-    def scalar_mul(self, points, scalars, output="extended", scalar_mont=False, out=None, flags=0):
-        """out[i] = [scalars[i]] points[i]  (`&ExtendedPoint * &Fr`, src/lib.rs:873-879)."""
+    # The scalar-multiplication entry points are variable-time in the scalar (zero window digits skip their addition,
+    # the table is indexed by the digit): the reference's `&ExtendedPoint * &Fr` is constant-time by policy
+    # (src/lib.rs:12-17) and names every variable-time routine `*_vartime` (:14-15) -- so do these.  Public scalars only.
+    def scalar_mul_vartime(self, points, scalars, output="extended", scalar_mont=False, out=None, flags=0):
+        """out[i] = [scalars[i]] points[i]  (`&ExtendedPoint * &Fr`, src/lib.rs:873-879); variable-time."""
         w, dt, f = self._out_fmt(output)
         sc = (scalars, 4, np.uint64) if scalar_mont else (scalars, 32, np.uint8)
         return self._call("jj_scalar_mul", [(points, EXT_W, np.uint64), sc], w, dt,
                           flags=f | flags | (L.JJ_SCALAR_MONT if scalar_mont else 0), out=out)
 
-    def scalar_mul_encoded(self, encodings, scalars, output="bytes", zip216=True):
+    def scalar_mul_encoded_vartime(self, encodings, scalars, output="bytes", zip216=True, check_subgroup=False, flags=0):
         """(out, ok): out[i] = [scalars[i]] AffinePoint::from_bytes(encodings[i]) -- wire format in (32-byte
         encodings, src/lib.rs:455-464), decoded on the device (src/lib.rs:541-627); ok[i] = 0 for a rejected
-        encoding (its output unit is unspecified)."""
+        encoding (its output unit is unspecified).  check_subgroup: the decode is SubgroupPoint::from_bytes
+        (src/lib.rs:1427-1429), i.e. ok[i] also requires is_torsion_free.  Variable-time."""
         w, dt, f = self._out_fmt(output)
+        f |= (0 if zip216 else L.JJ_PRE_ZIP216) | (L.JJ_CHECK_SUBGROUP if check_subgroup else 0) | flags
         return self._call("jj_scalar_mul_encoded", [(encodings, 32, np.uint8), (scalars, 32, np.uint8)], w, dt,
-                          flags=f | (0 if zip216 else L.JJ_PRE_ZIP216), ok=True)
+                          flags=f, ok=True)
 
-    def scalar_mul_fixed(self, base_affine, scalars, output="extended", scalar_mont=False, out=None):
-        """out[i] = [scalars[i]] base  (`&AffinePoint * &Fr`, src/lib.rs:1109-1115), one shared base."""
+    def scalar_mul_fixed_vartime(self, base_affine, scalars, output="extended", scalar_mont=False, out=None):
+        """out[i] = [scalars[i]] base  (`&AffinePoint * &Fr`, src/lib.rs:1109-1115), one shared base; variable-time."""
         w, dt, f = self._out_fmt(output)
         base = np.ascontiguousarray(base_affine, dtype=np.uint64).reshape(1, AFF_W)
         if scalar_mont:
@@ -234,7 +245,17 @@ class Engine:
         return o
 
     def batch_normalize(self, p, out=None):
+        """ExtendedPoint::batch_normalize (src/lib.rs:840-858): ExtendedPoint -> AffinePoint."""
         return self._call("jj_batch_normalize", [(p, EXT_W, np.uint64)], AFF_W, out=out)
+
+    def batch_normalize_extended(self, p, in_place=False):
+        """batch_normalize (src/lib.rs:1084-1107): the points themselves become (u/z, v/z, 1, u/z, v/z); in_place
+        overwrites `p` like the reference's `&mut [ExtendedPoint]`."""
+        return self._call("jj_batch_normalize_extended", [(p, EXT_W, np.uint64)], EXT_W, out=p if in_place else None)
+
+    def mul_by_cofactor(self, p, out=None):
+        """ExtendedPoint::mul_by_cofactor (src/lib.rs:722-724)."""
+        return self._call("jj_mul_by_cofactor", [(p, EXT_W, np.uint64)], EXT_W, out=out)
 
     def affine_to_bytes(self, a, out=None):
         return self._call("jj_affine_to_bytes", [(a, AFF_W, np.uint64)], 32, np.uint8, out=out)
@@ -244,12 +265,18 @@ class Engine:
         return self._call("jj_batch_from_bytes", [(enc, 32, np.uint8)], AFF_W, ok=True,
                           flags=0 if zip216 else L.JJ_PRE_ZIP216)
 
-    def _flag(self, name, p):
-        o = self._call(name, [(p, EXT_W, np.uint64)], 1, np.uint8)
+    def _flag(self, name, p, flags=0):
+        o = self._call(name, [(p, EXT_W, np.uint64)], 1, np.uint8, flags=flags)
         return o if isinstance(o, DeviceArray) else o.reshape(-1)
 
-    def is_torsion_free(self, p):
-        return self._flag("jj_is_torsion_free", p)
+    def is_torsion_free(self, p, ladder=False):
+        """ExtendedPoint::is_torsion_free (src/lib.rs:709-711).  Default: the order-8 pairing test (csrc/torsion.cuh);
+        ladder=True decides by the reference's own [r]P == O (the cross-check, ~7x the work)."""
+        return self._flag("jj_is_torsion_free", p, L.JJ_TORSION_LADDER if ladder else 0)
+
+    def is_prime_order(self, p):
+        """ExtendedPoint::is_prime_order (src/lib.rs:717-719)."""
+        return self._flag("jj_is_prime_order", p)
 
     def is_identity(self, p):
         return self._flag("jj_is_identity", p)
@@ -318,6 +345,7 @@ class Engine:
     def comm_init(self, nranks, rank, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         self._check(self.lib.jj_comm_init(self.ctx, nranks, rank, buf))
+        self.nranks, self.rank = nranks, rank
 
     def ipc_export(self, darr):
         """64-byte CUDA IPC handle of a DeviceArray (to be sent to the peer processes)."""
@@ -342,13 +370,35 @@ class Engine:
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self._check(self.lib.jj_comm_set_peer_outputs(self.ctx, arr, len(ptrs)))
 
-    def scalar_mul_sharded(self, points_local, scalars_local, out_all, output="extended", async_=False):
-        """This rank's shard + all-gather of every rank's results into out_all (device)."""
+    def scalar_mul_sharded_vartime(self, points_local, scalars_local, out_all, output="extended", async_=False,
+                                   n_total=None, out_local_host=None):
+        """This rank's block + all-gather of every rank's results into out_all (device).  points/scalars hold this
+        rank's block only: DeviceArrays, or host arrays (staged in chunks that overlap the kernels).  n_total: size of
+        the whole batch when the blocks are ragged (block partition of shard_range); default: equal blocks.
+        out_local_host: optional host array receiving this rank's own block of results."""
         w, dt, f = self._out_fmt(output)
-        f |= L.JJ_DEVICE_PTRS | (L.JJ_ASYNC if async_ else 0)
+        dev = isinstance(points_local, DeviceArray)
+        if isinstance(scalars_local, DeviceArray) != dev:
+            raise ValueError("points and scalars must both be DeviceArrays or both host arrays")
+        f |= (L.JJ_DEVICE_PTRS if dev else 0) | (L.JJ_ASYNC if async_ and dev else 0)
         n_local = points_local.shape[0]
-        self._check(self.lib.jj_scalar_mul_sharded(self.ctx, points_local.ptr, scalars_local.ptr, out_all.ptr,
-                                                   n_local, f))
+        if scalars_local.shape[0] != n_local:
+            raise JubjubError(-1, f"length mismatch: {scalars_local.shape[0]} != {n_local}")
+        if out_local_host is not None and (out_local_host.shape != (n_local, w) or out_local_host.dtype != np.dtype(dt)
+                                           or not out_local_host.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"out_local_host must be a contiguous ({n_local}, {w}) {np.dtype(dt)} array")
+        if not dev:
+            points_local = np.ascontiguousarray(points_local, dtype=np.uint64)
+            scalars_local = np.ascontiguousarray(scalars_local, dtype=np.uint8)
+        hp = out_local_host.ctypes.data if out_local_host is not None else None
+        if n_total is None:
+            if out_local_host is None and dev:
+                self._check(self.lib.jj_scalar_mul_sharded(self.ctx, points_local.ptr, scalars_local.ptr, out_all.ptr,
+                                                           n_local, f))
+                return out_all
+            n_total = n_local * self.nranks
+        self._check(self.lib.jj_scalar_mul_sharded_n(self.ctx, self._ptr(points_local), self._ptr(scalars_local),
+                                                     out_all.ptr, hp, n_total, f))
         return out_all
 
 

@@ -11,6 +11,11 @@ return `(value, is_some)` like `CtOption` (src/fr.rs:268-292, 438-540), a length
 (`assert_eq!`, src/lib.rs:841), `ExtendedPoint.__eq__` is projective equality (src/lib.rs:153-163),
 scalar multiplication takes `Fr` in Montgomery form and ignores nothing but what `Fr` cannot hold.
 There is no CPU arithmetic here: without a B200 the engine constructor raises.
+
+Constant time: the reference's `*` is constant-time by policy (src/lib.rs:12-17); the batch engine's scalar
+multiplication is NOT (zero window digits skip their addition).  The explicit methods are therefore named
+`mul_vartime` / `batch_mul_vartime`, following the reference's naming rule (src/lib.rs:14-15), and the `*` operator
+on points refuses to run until the caller has acknowledged this once with `acknowledge_vartime()`.
 """
 import numpy as np
 
@@ -18,6 +23,21 @@ from .engine import default_engine
 
 _GEN_RAW = (0x62EDCBB8BF3787C88B0F03DDD60A8187CAF55D1B29BF81AFE4B3D35DF1A7ADFE, 11)  # src/lib.rs:1380-1396
 _EDWARDS_D2_RAW = 0x552631CE97F45691EBFB240FCD7AFFA8525AFEDA6EAF3A4C020CBFADAC687D62  # 2d, src/lib.rs:407-412
+
+
+_VARTIME_ACK = False
+
+
+def acknowledge_vartime():
+    """Opt in to `point * scalar` operators: they run the variable-time batch kernels (public scalars only)."""
+    global _VARTIME_ACK
+    _VARTIME_ACK = True
+
+
+def _need_ack():
+    if not _VARTIME_ACK:
+        raise RuntimeError("point * scalar runs a variable-time kernel (the reference's `*` is constant-time, "
+                           "src/lib.rs:12-17): use mul_vartime(), or call jubjub_b200.types.acknowledge_vartime() once")
 
 
 def _limbs(x):
@@ -265,13 +285,17 @@ class AffinePoint:
 
     __hash__ = None
 
+    def mul_vartime(self, k):
+        """`&AffinePoint * &Fr` (src/lib.rs:1109-1115), variable-time; one shared base uses the fixed-base kernel."""
+        if len(self) == 1:
+            return ExtendedPoint(self.eng.scalar_mul_fixed_vartime(self.data, k.limbs, scalar_mont=True), self.eng)
+        return self.to_extended().mul_vartime(k)
+
     def __mul__(self, k):
-        """`&AffinePoint * &Fr` (src/lib.rs:1109-1115); one shared base uses the fixed-base kernel."""
         if not isinstance(k, Fr):
             return NotImplemented
-        if len(self) == 1:
-            return ExtendedPoint(self.eng.scalar_mul_fixed(self.data, k.limbs, scalar_mont=True), self.eng)
-        return self.to_extended() * k
+        _need_ack()
+        return self.mul_vartime(k)
 
     def mul_by_cofactor(self):
         return self.to_extended().mul_by_cofactor()
@@ -342,19 +366,24 @@ class ExtendedPoint:
         d[:, 12:16] = self.eng.fe_neg("fq", self.data[:, 12:16])
         return ExtendedPoint(d, self.eng)
 
+    def mul_vartime(self, k):
+        """`&ExtendedPoint * &Fr` (src/lib.rs:873-879), variable-time in the scalar."""
+        self._same(k)
+        return ExtendedPoint(self.eng.scalar_mul_vartime(self.data, k.limbs, scalar_mont=True), self.eng)
+
     def __mul__(self, k):
-        """`&ExtendedPoint * &Fr` (src/lib.rs:873-879)."""
         if not isinstance(k, Fr):
             return NotImplemented
-        self._same(k)
-        return ExtendedPoint(self.eng.scalar_mul(self.data, k.limbs, scalar_mont=True), self.eng)
+        _need_ack()
+        return self.mul_vartime(k)
 
     def multiply_bits(self, by):
         """[k]P for 32 little-endian bytes per point, top four bits ignored (src/lib.rs:381-385)."""
-        return ExtendedPoint(self.eng.scalar_mul(self.data, np.ascontiguousarray(by, dtype=np.uint8).reshape(-1, 32)), self.eng)
+        return ExtendedPoint(self.eng.scalar_mul_vartime(self.data, np.ascontiguousarray(by, dtype=np.uint8).reshape(-1, 32)), self.eng)
 
     def mul_by_cofactor(self):
-        return self.double().double().double()
+        """src/lib.rs:722-724."""
+        return ExtendedPoint(self.eng.mul_by_cofactor(self.data), self.eng)
 
     def is_identity(self):
         return self.eng.is_identity(self.data)
@@ -366,7 +395,8 @@ class ExtendedPoint:
         return self.eng.is_torsion_free(self.data)
 
     def is_prime_order(self):
-        return self.is_torsion_free() & (1 - self.is_identity())
+        """src/lib.rs:717-719."""
+        return self.eng.is_prime_order(self.data)
 
     def to_affine(self):
         return AffinePoint(self.eng.batch_normalize(self.data), self.eng)
@@ -388,13 +418,15 @@ class ExtendedPoint:
 
 # ---- free functions ---------------------------------------------------------------------------------
 def batch_normalize(points):
-    """jubjub::batch_normalize (src/lib.rs:1084-1107): ExtendedPoint batch -> AffinePoint batch."""
-    return points.to_affine()
+    """jubjub::batch_normalize (src/lib.rs:1084-1107): normalises the ExtendedPoint batch IN PLACE (z = 1, t1 = u,
+    t2 = v, like the reference's `&mut [ExtendedPoint]`) and returns the AffinePoint batch."""
+    points.eng.batch_normalize_extended(points.data, in_place=True)
+    return AffinePoint(points.data[:, :8], points.eng)
 
 
-def batch_mul(points, scalars):
-    """New batch entry point: points[i] * scalars[i] (ExtendedPoint x Fr)."""
-    return points * scalars
+def batch_mul_vartime(points, scalars):
+    """New batch entry point: points[i] * scalars[i] (ExtendedPoint x Fr); variable-time in the scalars."""
+    return points.mul_vartime(scalars)
 
 
 def batch_add(p, q):
@@ -403,4 +435,4 @@ def batch_add(p, q):
 
 
 __all__ = ["Fq", "Fr", "AffinePoint", "ExtendedPoint", "AffineNielsPoint", "ExtendedNielsPoint", "batch_normalize",
-           "batch_mul", "batch_add", "L"]
+           "batch_mul_vartime", "batch_add", "acknowledge_vartime"]

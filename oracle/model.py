@@ -121,6 +121,35 @@ def pmul(p, k):
     return acc
 
 
+def pmul_fast(p, k):
+    """[k]P, same value as pmul, without a modular inversion per step: projective (X : Y : Z) twisted-Edwards
+    arithmetic with the unified addition law (add-2008-bbjlp, a = -1), one inversion at the end.  Independent of the
+    C oracle and of the kernels (they use extended coordinates with Niels tables)."""
+    if k == 0:
+        return IDENTITY
+    x1, y1 = p
+    X, Y, Z = 0, 1, 1
+    for i in reversed(range(k.bit_length())):
+        # doubling (dbl-2008-bbjlp, a = -1)
+        B = (X + Y) * (X + Y) % Q
+        C, Dd = X * X % Q, Y * Y % Q
+        E = (-C) % Q
+        F = (E + Dd) % Q
+        H = Z * Z % Q
+        J = (F - 2 * H) % Q
+        X, Y, Z = (B - C - Dd) * J % Q, F * (E - Dd) % Q, F * J % Q
+        if (k >> i) & 1:  # mixed addition with the affine (x1, y1)
+            C, Dd = X * x1 % Q, Y * y1 % Q
+            E = D * C % Q * Dd % Q
+            B = Z * Z % Q
+            F, G = (B - E) % Q, (B + E) % Q
+            X3 = Z * F % Q * ((X + Y) * (x1 + y1) - C - Dd) % Q
+            Y3 = Z * G % Q * (Dd + C) % Q  # Dd - a*C with a = -1
+            X, Y, Z = X3, Y3, F * G % Q
+    zi = pow(Z, -1, Q)
+    return (X * zi % Q, Y * zi % Q)
+
+
 def scalar_from_bytes_ref(b32):
     """The integer the reference's multiply() actually uses: low 252 bits
     (src/lib.rs:363-372: MSB-first bits, first 4 skipped)."""

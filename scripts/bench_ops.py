@@ -52,14 +52,14 @@ def main():
     k = eng.fe_to_bytes("fr", eng.fe_stream("fr", SEED0 + 2, n, device=True))
     gen = generator(eng)
     p = eng.empty((n, 20))
-    rec("scalar_mul_fixed", timed(eng, lambda: eng.scalar_mul_fixed(gen, t, out=p), reps=3), 192)
+    rec("scalar_mul_fixed", timed(eng, lambda: eng.scalar_mul_fixed_vartime(gen, t, out=p), reps=3), 192)
     q = eng.point_double(p)
     o = eng.empty((n, 20))
     rec("point_double", timed(eng, lambda: eng._check(eng.lib.jj_point_double(eng.ctx, p.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 320)
     rec("point_add (ext+ext)", timed(eng, lambda: eng._check(eng.lib.jj_point_add(eng.ctx, p.ptr, q.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 480)
     nq = eng.point_to_niels(q)
     rec("point_add_niels", timed(eng, lambda: eng._check(eng.lib.jj_point_add_niels(eng.ctx, p.ptr, nq.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 448)
-    rec("scalar_mul (variable base)", timed(eng, lambda: eng.scalar_mul(p, k, out=o, flags=A), reps=3), 352)
+    rec("scalar_mul (variable base)", timed(eng, lambda: eng.scalar_mul_vartime(p, k, out=o, flags=A), reps=3), 352)
     aff = eng.empty((n, 8))
     rec("batch_normalize", timed(eng, lambda: eng.batch_normalize(o, out=aff)), 224)
     enc = eng.empty((n, 32), np.uint8)
@@ -68,11 +68,26 @@ def main():
     rec("batch_from_bytes", timed(eng, lambda: eng._check(eng.lib.jj_batch_from_bytes(
         eng.ctx, enc.ptr, back.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS)), reps=2, warm=1), 96)
     flg = eng.empty((n, 1), np.uint8)
-    rec("is_torsion_free", timed(eng, lambda: eng._check(eng.lib.jj_is_torsion_free(
-        eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS)), reps=2, warm=1), 161)
+    rec("is_torsion_free (pairing)", timed(eng, lambda: eng._check(eng.lib.jj_is_torsion_free(
+        eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS | A)), reps=3, warm=1), 97)
+    rec("is_torsion_free (ladder [r]P)", timed(eng, lambda: eng._check(eng.lib.jj_is_torsion_free(
+        eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS | A | jj.JJ_TORSION_LADDER)), reps=2, warm=1), 161)
+    rec("is_prime_order", timed(eng, lambda: eng._check(eng.lib.jj_is_prime_order(
+        eng.ctx, p.ptr, flg.ptr, n, jj.JJ_DEVICE_PTRS | A)), reps=3, warm=1), 97)
+    rec("mul_by_cofactor", timed(eng, lambda: eng._check(eng.lib.jj_mul_by_cofactor(
+        eng.ctx, p.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 320)
     outb = eng.empty((n, 32), np.uint8)
-    rec("scalar_mul_encoded (bytes->bytes)", timed(eng, lambda: eng._check(eng.lib.jj_scalar_mul_encoded(
-        eng.ctx, enc.ptr, k.ptr, outb.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS | jj.JJ_OUT_BYTES)), reps=2, warm=1), 97)
+    enc_call = lambda f: eng._check(eng.lib.jj_scalar_mul_encoded(  # noqa: E731
+        eng.ctx, enc.ptr, k.ptr, outb.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS | A | jj.JJ_OUT_BYTES | f))
+    rec("scalar_mul_encoded (bytes->bytes)", timed(eng, lambda: enc_call(0), reps=2, warm=1), 97)
+    rec("scalar_mul_encoded + subgroup check", timed(eng, lambda: enc_call(jj.JJ_CHECK_SUBGROUP), reps=2, warm=1), 97)
+    for v, name in ((200, "fused normalise epilogue"), (201, "separate normalise pass")):
+        eng.set_scalar_mul_variant(v)
+        rec(f"scalar_mul -> bytes ({name})", timed(eng, lambda: eng._check(eng.lib.jj_scalar_mul(
+            eng.ctx, p.ptr, k.ptr, outb.ptr, n, jj.JJ_DEVICE_PTRS | A | jj.JJ_OUT_BYTES)), reps=3, warm=1), 224)
+    eng.set_scalar_mul_variant(24)
+    rec("scalar_mul (24 warps/SM)", timed(eng, lambda: eng.scalar_mul_vartime(p, k, out=o, flags=A), reps=3), 352)
+    eng.set_scalar_mul_variant(0)
     # launch-bound chain: 48 small field batches (n = 4096) eagerly vs replayed as one CUDA graph
     m = 4096
     x, y, t2 = eng.fe_stream("fq", 1, m, device=True), eng.fe_stream("fq", 2, m, device=True), eng.empty((m, 4))

@@ -50,7 +50,7 @@ def main():
     gen_m = np.concatenate([eng.fe_from_bytes("fq", gen[:, :4].view(np.uint8).reshape(1, 32))[0],
                             eng.fe_from_bytes("fq", gen[:, 4:].view(np.uint8).reshape(1, 32))[0]], axis=1)
     fo = eng.empty((n, 20))
-    ms = timed(eng, lambda: eng.scalar_mul_fixed(gen_m, t, out=fo), reps=3)
+    ms = timed(eng, lambda: eng.scalar_mul_fixed_vartime(gen_m, t, out=fo), reps=3)
     out["fixed_base"] = {"n": n, "ms": ms, "per_s": n / ms * 1e3}
     print(f"fixed-base n={n}: {ms:.2f} ms  {n / ms * 1e3:.3e}/s", flush=True)
     pts = fo
@@ -60,7 +60,7 @@ def main():
     for v in (11, 13, 21):
         eng.set_scalar_mul_variant(v)
         try:
-            ms = timed(eng, lambda: eng.scalar_mul(pts, k, out=o, flags=jj.JJ_ASYNC), reps=2)
+            ms = timed(eng, lambda: eng.scalar_mul_vartime(pts, k, out=o, flags=jj.JJ_ASYNC), reps=2)
             out["variants"][v] = {"ms": ms, "per_s": n / ms * 1e3}
             print(f"variant {v}: {ms:.2f} ms  {n / ms * 1e3:.3e} scalar-mul/s", flush=True)
         except Exception as e:  # noqa: BLE001

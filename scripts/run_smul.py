@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--logn", type=int, default=17)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--what", default="smul", choices=["smul", "fixed", "fqmul"])
+    ap.add_argument("--what", default="smul", choices=["smul", "fixed", "fqmul", "torsion"])
     a = ap.parse_args()
     eng = jj.Engine(0)
     n = 1 << a.logn
@@ -37,14 +37,20 @@ def main():
     k = eng.fe_to_bytes("fr", eng.fe_stream("fr", SEED0 + 2, n, device=True))
     if a.what == "fixed":
         for _ in range(a.reps):
-            eng.scalar_mul_fixed(generator(eng), k)
+            eng.scalar_mul_fixed_vartime(generator(eng), k)
         return
-    pts = eng.scalar_mul_fixed(generator(eng), t)
+    pts = eng.scalar_mul_fixed_vartime(generator(eng), t)
+    if a.what == "torsion":
+        for _ in range(a.reps):
+            eng.timer_start()
+            eng.is_torsion_free(pts)
+            print(f"is_torsion_free n={n}: {eng.timer_stop():.3f} ms")
+        return
     eng.set_scalar_mul_variant(a.variant)
     o = eng.empty((n, 20))
     for _ in range(a.reps):
         eng.timer_start()
-        eng.scalar_mul(pts, k, out=o, flags=jj.JJ_ASYNC)
+        eng.scalar_mul_vartime(pts, k, out=o, flags=jj.JJ_ASYNC)
         ms = eng.timer_stop()
         print(f"n={n} variant={a.variant}: {ms:.3f} ms  {n / ms * 1e3:.4e}/s")
 

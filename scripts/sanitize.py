@@ -16,18 +16,22 @@ for f in ("fq", "fr"):
     eng.fe_invert(f, a[:64]); eng.fe_sqrt(f, a[:64]); eng.fe_from_bytes(f, eng.fe_to_bytes(f, a))
 g = generator(eng)
 k = eng.fe_to_bytes("fr", eng.fe_stream("fr", SEED0 + 2, n))
-p = eng.scalar_mul_fixed(g, k)
-eng.set_scalar_mul_variant(100); eng.scalar_mul_fixed(g, k[:100]); eng.set_scalar_mul_variant(0)
+p = eng.scalar_mul_fixed_vartime(g, k)
+eng.set_scalar_mul_variant(100); eng.scalar_mul_fixed_vartime(g, k[:100]); eng.set_scalar_mul_variant(0)
 q = eng.point_double(p)
 eng.point_add(p, q); eng.point_add_niels(p, eng.point_to_niels(q)); eng.point_add_affine_niels(p, eng.affine_to_niels(eng.batch_normalize(q)))
-for v in (0, 1, 5, 15):
+for v in (0, 24, 5, 200, 201):
     eng.set_scalar_mul_variant(v)
-    out = eng.scalar_mul(p, k, output="bytes")
+    out = eng.scalar_mul_vartime(p, k, output="bytes")
+    dev = eng.scalar_mul_vartime(eng.to_device(p), eng.to_device(k), output="bytes").download()
+    assert (dev == out).all()
 eng.set_scalar_mul_variant(0)
 pts, ok = eng.batch_from_bytes(out)
 assert ok.all()
-eng.is_torsion_free(p[:64]); eng.is_identity(p); eng.is_small_order(p)
-d = eng.to_device(p); eng.scalar_mul(d, eng.to_device(k), output="affine").download()
+eng.is_torsion_free(p); eng.is_torsion_free(p[:64], ladder=True); eng.is_prime_order(p); eng.is_identity(p); eng.is_small_order(p)
+eng.mul_by_cofactor(p); eng.batch_normalize_extended(q)
+enc, ok2 = eng.scalar_mul_encoded_vartime(out, k, check_subgroup=True)
+d = eng.to_device(p); eng.scalar_mul_vartime(d, eng.to_device(k), output="affine").download()
 # chains longer than one element per thread (Montgomery-trick kernels) at a size compute-sanitizer finishes quickly:
 # the grids are capped at one 128-thread block per 128 elements, so force chains by calling with few elements is not
 # possible -- these calls cover the single-element chains, the long chains are covered by tests/test_gpu_parity.py

@@ -23,7 +23,7 @@ int main(int argc, char** argv) {
     if (!f) return 3;
     try {
         Engine eng(0);
-        auto prod = eng.batch_mul(p, k);                       // (p * k) element-wise
+        auto prod = eng.batch_mul_vartime(p, k);                       // (p * k) element-wise
         auto enc = eng.batch_to_bytes(eng.batch_normalize(prod));
         for (uint64_t i = 0; i < n; i++)
             if (std::memcmp(enc[i].data(), want[i].data(), 32) != 0) {
@@ -36,13 +36,26 @@ int main(int argc, char** argv) {
         if (std::memcmp(a.data(), d.data(), n * sizeof(AffinePoint)) != 0) return 4;
         // wire format in and out: encode p, then decode + multiply + encode on the device
         std::vector<uint8_t> some;
-        auto enc2 = eng.batch_mul_encoded(eng.batch_to_bytes(eng.batch_normalize(p)), k, some);
+        auto enc2 = eng.batch_mul_encoded_vartime(eng.batch_to_bytes(eng.batch_normalize(p)), k, some);
         for (uint64_t i = 0; i < n; i++)
             if (!some[i] || std::memcmp(enc2[i].data(), want[i].data(), 32) != 0) return 7;
+        // in-place batch_normalize (src/lib.rs:1084-1107), mul_by_cofactor = three doublings, subgroup flags
+        auto pn = p;
+        auto an = eng.batch_normalize_in_place(pn);
+        auto a0 = eng.batch_normalize(p);
+        if (std::memcmp(an.data(), a0.data(), n * sizeof(AffinePoint)) != 0) return 8;
+        for (uint64_t i = 0; i < n; i++)
+            if (std::memcmp(&pn[i].t1, &pn[i].u, 32) != 0 || std::memcmp(&pn[i].t2, &pn[i].v, 32) != 0) return 9;
+        auto c8 = eng.batch_mul_by_cofactor(p);
+        auto d3 = eng.batch_double(eng.batch_double(eng.batch_double(p)));
+        if (std::memcmp(c8.data(), d3.data(), n * sizeof(ExtendedPoint)) != 0) return 10;
+        auto tf = eng.batch_is_torsion_free(c8), po = eng.batch_is_prime_order(c8);
+        for (uint64_t i = 0; i < n; i++)
+            if (!tf[i] || !po[i]) return 11;  // [8]P lies in the prime-order subgroup (and is not O for these inputs)
         bool threw = false;
         try {
             k.pop_back();
-            eng.batch_mul(p, k);
+            eng.batch_mul_vartime(p, k);
         } catch (const Error& e) {
             threw = e.code == JJ_ERR_INVALID_ARG;
         }

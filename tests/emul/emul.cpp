@@ -37,6 +37,13 @@ extern "C" void emul_fe_op(int which, int op, const void* a, const void* b, void
 }
 
 #include "../../jubjub_b200/csrc/slotmul.cuh"
+#include "../../jubjub_b200/csrc/torsion.cuh"
+
+// pairing-based is_torsion_free (torsion.cuh) on ExtendedPoint inputs
+extern "C" void emul_is_torsion_free(const void* p_, uint8_t* out, size_t n) {
+    const ext_point* p = (const ext_point*)p_;
+    for (size_t i = 0; i < n; i++) out[i] = point_is_torsion_free(p[i].u, p[i].v, p[i].z) ? 1 : 0;
+}
 
 // op: 0 double, 1 add (ext+ext), 2 sub (ext-ext), 3 add ext-niels, 4 sub ext-niels,
 //     5 add affine-niels, 6 sub affine-niels, 7 to_niels (ext), 8 to_niels (affine), 9 neg

@@ -251,18 +251,20 @@ def _smul_case(oracle, n):
     return p, k
 
 
-@pytest.mark.parametrize("variant", list(range(0, 28)))
+# what ships: the default mapping (0 = 13), the two A/B mappings (24, 5 warps-per-SM variants), and the default mapping
+# with the fused normalise epilogue forced on / off for converted outputs (200 / 201)
+@pytest.mark.parametrize("variant", [0, 13, 24, 5, 200, 201])
 def test_scalar_mul_variants(eng, oracle, variant):
     eng.set_scalar_mul_variant(variant)
     try:
-        p, k = _smul_case(oracle, 1200 if variant == 0 else 300)
+        p, k = _smul_case(oracle, 1200 if variant in (0, 200) else 300)
         want_ext = oracle.scalar_mul(p, k)
         want_aff = oracle.batch_normalize(want_ext)
-        got = eng.scalar_mul(p, k)
+        got = eng.scalar_mul_vartime(p, k)
         assert oracle.ext_eq(got, want_ext).all()  # projective equality, src/lib.rs:153-163
         assert (oracle.batch_normalize(got) == want_aff).all()
-        assert (eng.scalar_mul(p, k, output="affine") == want_aff).all()
-        assert (eng.scalar_mul(p, k, output="bytes") == oracle.affine_to_bytes(want_aff)).all()
+        assert (eng.scalar_mul_vartime(p, k, output="affine") == want_aff).all()
+        assert (eng.scalar_mul_vartime(p, k, output="bytes") == oracle.affine_to_bytes(want_aff)).all()
     finally:
         eng.set_scalar_mul_variant(0)
 
@@ -270,7 +272,7 @@ def test_scalar_mul_variants(eng, oracle, variant):
 def test_scalar_mul_vs_bigint_model(eng, oracle):
     p, k = _smul_case(oracle, 40)
     vals = oracle.fe_to_bytes(FQ, oracle.batch_normalize(p).reshape(-1, 4)).reshape(-1, 64)
-    got = eng.scalar_mul(p, k, output="bytes")
+    got = eng.scalar_mul_vartime(p, k, output="bytes")
     for i in range(len(p)):
         u = int.from_bytes(bytes(vals[i, :32]), "little")
         v = int.from_bytes(bytes(vals[i, 32:]), "little")
@@ -281,7 +283,7 @@ def test_scalar_mul_montgomery_scalars(eng, oracle):
     """`&ExtendedPoint * &Fr` takes the scalar in Montgomery form and calls to_bytes (src/lib.rs:877)."""
     p = _points(oracle, 200)
     s = oracle.fe_stream(FR, 99, len(p))
-    got = eng.scalar_mul(p, s, scalar_mont=True, output="affine")
+    got = eng.scalar_mul_vartime(p, s, scalar_mont=True, output="affine")
     assert (got == oracle.batch_normalize(oracle.scalar_mul(p, oracle.fe_to_bytes(FR, s)))).all()
 
 
@@ -290,14 +292,14 @@ def test_mul_consistency_and_assoc(eng, oracle):
     p = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(affine_raw(oracle, [K.TEST_POINT_RAW])))
     a, b, c = fe(K.MULC_A), fe(K.MULC_B), fe(K.MULC_C)
     assert (eng.fe_mul("fr", a, b) == c).all()
-    pc = eng.scalar_mul(p, c, scalar_mont=True)
-    pab = eng.scalar_mul(eng.scalar_mul(p, a, scalar_mont=True), b, scalar_mont=True)
+    pc = eng.scalar_mul_vartime(p, c, scalar_mont=True)
+    pab = eng.scalar_mul_vartime(eng.scalar_mul_vartime(p, a, scalar_mont=True), b, scalar_mont=True)
     assert oracle.ext_eq(pc, pab)[0]
     assert (eng.batch_normalize(pc) == eng.batch_normalize(pab)).all()
     aff = eng.batch_normalize(p)
-    assert (eng.scalar_mul_fixed(aff, c, scalar_mont=True, output="affine") == eng.batch_normalize(pab)).all()
-    lhs = eng.scalar_mul(eng.scalar_mul(p, scalar_bytes(1000)), scalar_bytes(3938))
-    assert oracle.ext_eq(lhs, eng.scalar_mul(p, scalar_bytes(3938000)))[0]
+    assert (eng.scalar_mul_fixed_vartime(aff, c, scalar_mont=True, output="affine") == eng.batch_normalize(pab)).all()
+    lhs = eng.scalar_mul_vartime(eng.scalar_mul_vartime(p, scalar_bytes(1000)), scalar_bytes(3938))
+    assert oracle.ext_eq(lhs, eng.scalar_mul_vartime(p, scalar_bytes(3938000)))[0]
 
 
 @pytest.mark.parametrize("variant", [0, 100])  # 0: 7-bit windows (216 KB table); 100: 4-bit windows (47 KB)
@@ -313,9 +315,9 @@ def _check_fixed(eng, oracle):
     k = np.concatenate([scalar_bytes(*EDGE_SCALARS), oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 5, 2000))])
     for base in (oracle.generator(), oracle.ext_to_affine(oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator())))):
         want = oracle.batch_normalize(oracle.scalar_mul_fixed(base, k))
-        assert (eng.scalar_mul_fixed(base, k, output="affine") == want).all()
-        assert (eng.batch_normalize(eng.scalar_mul_fixed(base, k)) == want).all()
-        assert (eng.scalar_mul_fixed(base, k, output="bytes") == oracle.affine_to_bytes(want)).all()
+        assert (eng.scalar_mul_fixed_vartime(base, k, output="affine") == want).all()
+        assert (eng.batch_normalize(eng.scalar_mul_fixed_vartime(base, k)) == want).all()
+        assert (eng.scalar_mul_fixed_vartime(base, k, output="bytes") == oracle.affine_to_bytes(want)).all()
 
 
 def test_serialization_golden(eng, oracle):
@@ -323,8 +325,8 @@ def test_serialization_golden(eng, oracle):
     g8 = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator()))
     want = b32(*K.SERIALIZED_MULTIPLES_OF_8G)
     k = scalar_bytes(*range(1, 17))
-    assert (eng.scalar_mul(np.repeat(g8, 16, axis=0), k, output="bytes") == want).all()
-    assert (eng.scalar_mul_fixed(oracle.ext_to_affine(g8), k, output="bytes") == want).all()
+    assert (eng.scalar_mul_vartime(np.repeat(g8, 16, axis=0), k, output="bytes") == want).all()
+    assert (eng.scalar_mul_fixed_vartime(oracle.ext_to_affine(g8), k, output="bytes") == want).all()
     # and by repeated addition, as the reference test walks it
     p = g8
     for i in range(16):
@@ -355,9 +357,50 @@ def test_batch_normalize_and_flags(eng, oracle):
     assert eng.is_identity(c).all()
     assert (eng.is_identity(p[:20]) == oracle.is_identity(p[:20])).all()
     assert (eng.is_torsion_free(p[:40]) == oracle.is_torsion_free(p[:40])).all()
+    assert (eng.is_torsion_free(p[:40], ladder=True) == oracle.is_torsion_free(p[:40])).all()
     g8 = oracle.ext_mul_by_cofactor(p[9:30])
     assert eng.is_torsion_free(g8).all()
     assert (eng.is_small_order(p[:40]) == oracle.is_small_order(p[:40])).all()
+    # is_prime_order (src/lib.rs:717-719): torsion free and not the identity; p[0] is the identity
+    want_po = oracle.is_torsion_free(p[:40]) & (1 - oracle.is_identity(p[:40]))
+    assert (eng.is_prime_order(p[:40]) == want_po).all() and eng.is_prime_order(p[:1])[0] == 0
+    assert eng.is_prime_order(g8).all()
+    # mul_by_cofactor (src/lib.rs:722-724): all 160 bytes
+    assert (eng.mul_by_cofactor(q) == oracle.ext_mul_by_cofactor(q)).all()
+
+
+def test_batch_normalize_extended_in_place(eng, oracle):
+    """The free function batch_normalize (src/lib.rs:1084-1107): the ExtendedPoints themselves are normalised
+    (z = 1, t1 = u, t2 = v), in place on the host and on the device; z = 0 ends as (0, 0, 1, 0, 0)."""
+    p = oracle.ext_double(oracle.ext_double(_points(oracle, 5000)))
+    p[7, 8:12] = 0
+    aff = oracle.batch_normalize(p)
+    one = np.repeat(oracle.fe_one(FQ), len(p), axis=0)
+    want = np.concatenate([aff, one, aff], axis=1)
+    assert (eng.batch_normalize_extended(p) == want).all()
+    q = p.copy()
+    out = eng.batch_normalize_extended(q, in_place=True)
+    assert out is q and (q == want).all() and (q[7, :8] == 0).all() and (q[7, 12:] == 0).all()
+    d = eng.to_device(p)
+    assert eng.batch_normalize_extended(d, in_place=True) is d and (d.download() == want).all()
+    import jubjub_b200.types as T
+
+    pts = T.ExtendedPoint(p.copy(), eng)
+    a = T.batch_normalize(pts)  # reference semantics: normalises `pts` and hands back the affine points
+    assert (a.data == aff).all() and (pts.data == want).all()
+
+
+def test_out_buffer_is_validated(eng, oracle):
+    """a caller-supplied `out` of the wrong shape or dtype must raise instead of being overrun."""
+    a, b = oracle.fe_stream(FQ, 1, 64), oracle.fe_stream(FQ, 2, 64)
+    with pytest.raises(ValueError):
+        eng.fe_mul("fq", a, b, out=np.empty((32, 4), np.uint64))
+    with pytest.raises(ValueError):
+        eng.fe_mul("fq", a, b, out=np.empty((64, 4), np.uint32))
+    with pytest.raises(ValueError):
+        eng.fe_mul("fq", eng.to_device(a), eng.to_device(b), out=eng.empty((64, 8)))
+    big = np.zeros((100, 4), np.uint64)
+    assert eng.fe_mul("fq", a, b, out=big) is big and (big[:64] == oracle.fe_batch(FQ, oracle.OP_MUL, a, b)).all()
 
 
 def test_batch_from_bytes(eng, oracle):
@@ -397,7 +440,7 @@ def test_batch_from_bytes_long_chains(eng, oracle):
     kind (non-canonical v = skipped zero denominator, off-curve v, flipped sign) scattered through the chains."""
     n = 2 * 75776 + 999
     t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 7, n))
-    enc = eng.affine_to_bytes(eng.batch_normalize(eng.scalar_mul_fixed(oracle.generator(), t)))
+    enc = eng.affine_to_bytes(eng.batch_normalize(eng.scalar_mul_fixed_vartime(oracle.generator(), t)))
     enc = enc.copy()
     enc[5::11, 0] ^= 1          # v + 1 (or - 1): mostly off the curve
     enc[3::97] = 0xFF           # non-canonical v
@@ -416,14 +459,14 @@ def test_scalar_mul_encoded(eng, oracle):
     n = 150000
     t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 17, n))
     k = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 18, n))
-    aff = eng.batch_normalize(eng.scalar_mul_fixed(oracle.generator(), t))
+    aff = eng.batch_normalize(eng.scalar_mul_fixed_vartime(oracle.generator(), t))
     enc = eng.affine_to_bytes(aff).copy()
     enc[11::37, 0] ^= 1        # mostly off the curve
     enc[5::113] = 0xFF         # non-canonical
     want_aff, wok = eng.batch_from_bytes(enc)     # decode parity itself is covered by test_batch_from_bytes*
     ext = np.concatenate([want_aff, np.repeat(oracle.fe_one(FQ), n, axis=0), want_aff], axis=1)
-    want = eng.scalar_mul(ext, k, output="bytes")
-    got, ok = eng.scalar_mul_encoded(enc, k)
+    want = eng.scalar_mul_vartime(ext, k, output="bytes")
+    got, ok = eng.scalar_mul_encoded_vartime(enc, k)
     assert (ok == wok).all() and 0.9 * n < ok.sum() < n
     assert (got[ok == 1] == want[ok == 1]).all()
     # against the oracle end to end on a sample: decode -> ladder -> normalise -> encode
@@ -433,34 +476,75 @@ def test_scalar_mul_encoded(eng, oracle):
     owant = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(oext, k[s])))
     assert (ok[s] == ook).all() and (got[s][ook == 1] == owant[ook == 1]).all()
     for output in ("affine", "extended"):
-        g2, ok2 = eng.scalar_mul_encoded(enc[:5000], k[:5000], output=output)
+        g2, ok2 = eng.scalar_mul_encoded_vartime(enc[:5000], k[:5000], output=output)
         a2 = g2 if output == "affine" else eng.batch_normalize(g2)
         assert (ok2 == wok[:5000]).all()
         assert (eng.affine_to_bytes(a2)[ok2 == 1] == want[:5000][ok2 == 1]).all()
-    gd, okd = eng.scalar_mul_encoded(eng.to_device(enc[:70000]), eng.to_device(k[:70000]))
+    gd, okd = eng.scalar_mul_encoded_vartime(eng.to_device(enc[:70000]), eng.to_device(k[:70000]))
     assert (okd.download().ravel() == wok[:70000]).all()
     assert (gd.download()[wok[:70000] == 1] == want[:70000][wok[:70000] == 1]).all()
 
 
-def test_is_torsion_free_large_batch_property(eng, oracle):
-    """2^18 points P_i = [t_i] G with G of order 8r (src/lib.rs:1380-1396): P_i is torsion free exactly when
-    8 | t_i (src/lib.rs:709-711) -- a size-independent check of the shared-scalar (width-5 NAF of r) kernel --
-    and every [8] P_i is torsion free; a sample is also compared with the oracle's bitwise ladder."""
-    n = 1 << 18
+def test_scalar_mul_encoded_subgroup_check(eng, oracle):
+    """JJ_CHECK_SUBGROUP: the decode is SubgroupPoint::from_bytes (src/lib.rs:1427-1429) -- ok[i] = decoded AND
+    torsion free -- and accepted units are multiplied as before.  Host (staged chunks) and device resident."""
+    n = 100000
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 21, n))
+    t[::3, 0] &= 0xF8  # a third of the points in the prime-order subgroup: [t]G with 8 | t
+    k = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 22, n))
+    pts = eng.scalar_mul_fixed_vartime(oracle.generator(), t)
+    enc = eng.affine_to_bytes(eng.batch_normalize(pts)).copy()
+    enc[13::41] = 0xFF  # some undecodable
+    _, dec_ok = eng.batch_from_bytes(enc)
+    want_ok = dec_ok & ((t[:, 0] & 7) == 0)
+    got, ok = eng.scalar_mul_encoded_vartime(enc, k, check_subgroup=True)
+    assert (ok == want_ok).all() and 0.25 * n < ok.sum() < 0.4 * n
+    plain, _ = eng.scalar_mul_encoded_vartime(enc, k)
+    assert (got[ok == 1] == plain[ok == 1]).all()
+    s = np.flatnonzero(ok)[:300]
+    want = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(pts[s], k[s])))
+    assert (got[s] == want).all()
+    assert (oracle.is_torsion_free(pts[:400]) == ((t[:400, 0] & 7) == 0)).all()  # the property used above, vs the oracle
+    gd, okd = eng.scalar_mul_encoded_vartime(eng.to_device(enc), eng.to_device(k), check_subgroup=True)
+    assert (okd.download().ravel() == want_ok).all() and (gd.download()[ok == 1] == got[ok == 1]).all()
+
+
+def test_is_torsion_free_full_size_all_cosets(eng, oracle):
+    """2^20 points (BASELINE size): P_i = [t_i] G with G of order 8r (src/lib.rs:1380-1396) is torsion free exactly
+    when 8 | t_i (src/lib.rs:709-711).  The pairing test (default), the reference-style [r]P == O kernel
+    (JJ_TORSION_LADDER) and that property must agree on every unit; then every coset P + T_j of prime-order points
+    over the reference's eight torsion points (src/lib.rs:1589-1677), in projective forms with z != 1, against the
+    oracle's bitwise ladder."""
+    n = 1 << 20
     t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 13, n))
     t[::5, 0] &= 0xF8  # make a fifth of the scalars multiples of 8
-    pts = eng.scalar_mul_fixed(oracle.generator(), t)
+    pts = eng.scalar_mul_fixed_vartime(oracle.generator(), t)
     flags = eng.is_torsion_free(pts)
     assert (flags == ((t[:, 0] & 7) == 0)).all() and 0.2 * n < flags.sum() < 0.4 * n
-    p8 = eng.point_double(eng.point_double(eng.point_double(pts)))
-    assert eng.is_torsion_free(p8).all()
+    assert (eng.is_torsion_free(pts, ladder=True) == flags).all()
+    p8 = eng.mul_by_cofactor(pts)
+    assert eng.is_torsion_free(p8).all() and eng.is_prime_order(p8).sum() >= n - 1
     assert (flags[:600] == oracle.is_torsion_free(pts[:600])).all()
+    # all eight cosets: P + T_j is torsion free only for T_j = O
+    m = 1 << 15
+    tors = oracle.affine_to_extended(affine_raw(oracle, K.EIGHT_TORSION_RAW))
+    tors_is_o = oracle.is_identity(tors)
+    assert tors_is_o.sum() == 1
+    base = eng.point_double(p8[:m])                      # prime order, z != 1
+    for j in range(8):
+        c = eng.point_add(base, np.repeat(tors[j:j + 1], m, axis=0))
+        f = eng.is_torsion_free(c)
+        assert (f == tors_is_o[j]).all(), j
+        assert (f[:64] == oracle.is_torsion_free(c[:64])).all(), j
+        assert (eng.is_torsion_free(c[:4096], ladder=True) == tors_is_o[j]).all(), j
+    small = np.concatenate([tors, eng.point_double(tors), oracle.identity(4)])
+    assert (eng.is_torsion_free(small) == oracle.is_torsion_free(small)).all()
 
 
 def test_find_eight_torsion_on_gpu(eng, oracle):
     """src/lib.rs:1680-1696: [r] G walks the 8-torsion subgroup."""
     g = oracle.affine_to_extended(affine_raw(oracle, [K.FULL_GENERATOR_RAW]))
-    t = eng.scalar_mul(g, b32(K.FR_MODULUS_BYTES))
+    t = eng.scalar_mul_vartime(g, b32(K.FR_MODULUS_BYTES))
     want = affine_raw(oracle, K.EIGHT_TORSION_RAW)
     cur = t
     for i in range(8):
@@ -476,7 +560,7 @@ def test_device_resident_and_in_place(eng, oracle):
     assert out is da and (da.download() == oracle.fe_batch(FQ, oracle.OP_MUL, a, b)).all()
     p, k = _smul_case(oracle, 500)
     dp, dk = eng.to_device(p), eng.to_device(k)
-    got = eng.scalar_mul(dp, dk, output="affine").download()
+    got = eng.scalar_mul_vartime(dp, dk, output="affine").download()
     assert (got == oracle.batch_normalize(oracle.scalar_mul(p, k))).all()
     dd = eng.point_double(dp, out=dp)
     assert (dd.download() == oracle.ext_double(p)).all()
@@ -484,13 +568,13 @@ def test_device_resident_and_in_place(eng, oracle):
 
 def test_empty_ragged_and_chunk_boundaries(eng, oracle):
     assert eng.fe_mul("fq", np.zeros((0, 4), np.uint64), np.zeros((0, 4), np.uint64)).shape == (0, 4)
-    assert eng.scalar_mul(np.zeros((0, 20), np.uint64), np.zeros((0, 32), np.uint8)).shape == (0, 20)
+    assert eng.scalar_mul_vartime(np.zeros((0, 20), np.uint64), np.zeros((0, 32), np.uint8)).shape == (0, 20)
     for n in (1, 31, 33, (1 << 17) - 1, (1 << 17) + 1, 3 * (1 << 17) + 5):  # staging chunk is 2^17 units
         a, b = oracle.fe_stream(FQ, 1, n), oracle.fe_stream(FQ, 2, n)
         assert (eng.fe_mul("fq", a, b) == oracle.fe_batch(FQ, oracle.OP_MUL, a, b)).all(), n
     p, k = _smul_case(oracle, 70)
     for n in (1, 31, 33, 79):
-        assert (eng.scalar_mul(p[:n], k[:n], output="affine") == oracle.batch_normalize(oracle.scalar_mul(p[:n], k[:n]))).all()
+        assert (eng.scalar_mul_vartime(p[:n], k[:n], output="affine") == oracle.batch_normalize(oracle.scalar_mul(p[:n], k[:n]))).all()
 
 
 def test_error_behaviour(eng, oracle):
@@ -507,6 +591,7 @@ def test_error_behaviour(eng, oracle):
     assert eng.lib.jj_fq_mul(eng.ctx, d.ptr + 8, d.ptr, d.ptr, 4, jj.JJ_DEVICE_PTRS) == -1  # misaligned
     assert b"aligned" in eng.lib.jj_last_error(eng.ctx)
     assert eng.lib.jj_set_scalar_mul_variant(eng.ctx, 99) == -1
+    assert eng.lib.jj_set_scalar_mul_variant(eng.ctx, 15) == -1  # experimental mappings are not in the default build
     ctx = C.c_void_p()
     assert eng.lib.jj_init(10_000, C.byref(ctx)) == -1
 
@@ -517,14 +602,14 @@ def test_full_size_linearity_1m(eng, oracle):
     n = 1 << 20
     g8 = oracle.ext_to_affine(oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator())))
     t = eng.fe_to_bytes("fr", eng.fe_stream("fr", M.SEED0 + 3, n, device=True))
-    pts = eng.scalar_mul_fixed(g8, t)  # P_i = [t_i] 8G, device resident
+    pts = eng.scalar_mul_fixed_vartime(g8, t)  # P_i = [t_i] 8G, device resident
     a = eng.fe_stream("fr", M.SEED0 + 2, n, device=True)
     b = eng.fe_stream("fr", M.SEED0 + 4, n, device=True)
     ab = eng.fe_add("fr", a, b)
-    pa = eng.scalar_mul(pts, a, scalar_mont=True)
-    pb = eng.scalar_mul(pts, b, scalar_mont=True)
+    pa = eng.scalar_mul_vartime(pts, a, scalar_mont=True)
+    pb = eng.scalar_mul_vartime(pts, b, scalar_mont=True)
     lhs = eng.batch_normalize(eng.point_add(pa, pb)).download()
-    rhs = eng.scalar_mul(pts, ab, scalar_mont=True, output="affine").download()
+    rhs = eng.scalar_mul_vartime(pts, ab, scalar_mont=True, output="affine").download()
     assert (lhs == rhs).all()
     idx = np.arange(0, n, n // 512)[:512]
     ph, ah = pts.download()[idx], oracle.fe_to_bytes(FR, a.download()[idx])
@@ -537,9 +622,9 @@ def test_full_size_fixed_base_1m(eng, oracle):
     n = 1 << 20
     gen = oracle.generator()
     k = eng.fe_to_bytes("fr", eng.fe_stream("fr", M.SEED0 + 2, n, device=True))
-    fixed = eng.scalar_mul_fixed(gen, k, output="affine").download()
+    fixed = eng.scalar_mul_fixed_vartime(gen, k, output="affine").download()
     pts = eng.to_device(np.repeat(oracle.affine_to_extended(gen), n, axis=0))
-    var = eng.scalar_mul(pts, k, output="affine").download()
+    var = eng.scalar_mul_vartime(pts, k, output="affine").download()
     assert (fixed == var).all()
     idx = np.arange(0, n, n // 256)[:256]
     kh = k.download()[idx]
@@ -551,10 +636,10 @@ def test_scalar_mul_differential_64k(eng, oracle):
     that bits 252..255 are exercised) compared unit by unit with the oracle's reference ladder."""
     n = 1 << 16
     t = eng.fe_to_bytes("fr", eng.fe_stream("fr", 7001, n))
-    p = eng.point_double(eng.scalar_mul_fixed(oracle.generator(), t))  # z != 1
+    p = eng.point_double(eng.scalar_mul_fixed_vartime(oracle.generator(), t))  # z != 1
     rng = np.random.default_rng(2024)
     k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)  # arbitrary top bits: ignored like multiply_bits
-    got = eng.scalar_mul(p, k, output="bytes")
+    got = eng.scalar_mul_vartime(p, k, output="bytes")
     want = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(p, k)))
     assert (got == want).all()
 
@@ -587,3 +672,45 @@ def test_cuda_graph_replay(eng, oracle):
         eng.sync()
         assert (x.download() == want).all()
     eng.graph_destroy(g)
+
+
+def test_cuda_graph_scratch_safety(oracle):
+    """a replayed graph must never write through a freed scratch pointer.  While a captured graph is alive
+    a call that would have to grow a main-stream scratch buffer fails (and the graph still replays correctly); calls
+    that cannot be captured (host pointers, allocation inside the capture) are refused and leave the capture usable."""
+    import jubjub_b200 as jj
+
+    eng = jj.Engine(0)  # own context: scratch sizes start from zero
+    try:
+        A = jj.JJ_ASYNC
+        n1, n2 = 3000, 400000
+        a = oracle.fe_stream(FQ, 41, n2)
+        a[5] = 0
+        d1, o1, ok1 = eng.to_device(a[:n1]), eng.empty((n1, 4)), eng.empty((n1, 1), np.uint8)
+        d2, o2, ok2 = eng.to_device(a), eng.empty((n2, 4)), eng.empty((n2, 1), np.uint8)
+        inv = lambda d, o, ok, n, f: eng.lib.jj_fq_invert(eng.ctx, d.ptr, o.ptr, ok.ptr, n, jj.JJ_DEVICE_PTRS | f)  # noqa: E731
+        want1, _ = oracle.fe_invert(FQ, a[:n1])
+        # capturing before the scratch exists: refused, nothing allocated inside the capture
+        eng._check(eng.lib.jj_graph_begin(eng.ctx))
+        assert inv(d1, o1, ok1, n1, A) == -1 and b"eagerly" in eng.lib.jj_last_error(eng.ctx)
+        assert eng.lib.jj_fq_mul(eng.ctx, a.ctypes.data, a.ctypes.data, a.ctypes.data, 8, 0) == -1  # host pointers
+        import ctypes as C
+
+        g0 = C.c_void_p()
+        assert eng.lib.jj_graph_end(eng.ctx, C.byref(g0)) == 0  # the (empty) capture ends cleanly
+        if g0.value:
+            eng.graph_destroy(g0)
+        assert inv(d1, o1, ok1, n1, 0) == 0  # eager run creates the scratch (n1 x 32 B)
+        g = eng.graph_capture(lambda: eng._check(inv(d1, o1, ok1, n1, A)))
+        # a larger batch would reallocate the scratch the graph's kernel node points at: refused while the graph lives
+        assert inv(d2, o2, ok2, n2, 0) == -1 and b"graph" in eng.lib.jj_last_error(eng.ctx)
+        o1.upload(np.zeros((n1, 4), np.uint64))
+        eng.graph_launch(g)
+        eng.sync()
+        assert (o1.download() == want1).all()
+        eng.graph_destroy(g)
+        assert inv(d2, o2, ok2, n2, 0) == 0  # allowed again once the graph is gone
+        assert (o2.download() == oracle.fe_invert(FQ, a)[0]).all()
+    finally:
+        eng.close()
+

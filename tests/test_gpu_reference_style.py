@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 def T():
     from jubjub_b200 import types
 
+    # `point * scalar` runs a variable-time kernel (the reference's `*` is constant-time, src/lib.rs:12-17): the
+    # operator refuses until the caller opts in; mul_vartime() is the explicitly named form
+    p = types.ExtendedPoint.identity()
+    if not types._VARTIME_ACK:
+        with pytest.raises(RuntimeError):
+            p * types.Fr.one()
+    assert p.mul_vartime(types.Fr.one()).is_identity()[0]
+    types.acknowledge_vartime()
     return types
 
 
@@ -51,6 +59,9 @@ def test_batch_normalize(T):  # src/lib.rs:1530-1575
     for i in range(10):
         assert expected[i] == T.AffinePoint(result.data[i:i + 1])
     assert T.ExtendedPoint.from_affine(result) == v
+    # the reference normalises `v` itself: z = 1, t1 = u, t2 = v (src/lib.rs:1088-1100)
+    assert (v.data[:, 8:12] == T.Fq.one(10).limbs).all()
+    assert (v.data[:, 12:16] == v.data[:, 0:4]).all() and (v.data[:, 16:20] == v.data[:, 4:8]).all()
 
 
 def test_eight_torsion_and_small_order(T):  # src/lib.rs:1589-1754

@@ -290,3 +290,80 @@ def test_emulated_sqrt_and_decode(built, oracle):
         lib.emul_from_bytes(P(allenc), P(got), P(ok), zip216, C.c_size_t(len(allenc)))
         want, wok = oracle.affine_from_bytes(allenc, zip216=bool(zip216))
         assert (ok == wok).all() and (got[ok == 1] == want[wok == 1]).all()
+
+
+def _torsion_cosets(oracle, n, seed):
+    """n prime-order points (random projective scaling) and, for each, its eight cosets P + T_j over the reference's
+    8-torsion table (src/lib.rs:1589-1677): (8n, 20) extended points, coset j of point i at row 8i + j."""
+    from tests.golden import reference_kats as K
+    from tests.helpers import affine_raw
+
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, seed, n))
+    p = oracle.ext_mul_by_cofactor(oracle.scalar_mul(np.repeat(g, n, axis=0), t))       # prime order, z != 1
+    tors = oracle.affine_to_extended(affine_raw(oracle, K.EIGHT_TORSION_RAW))           # T_0 .. T_7 (T_7 or so = O)
+    pts = np.concatenate([oracle.ext_add(np.repeat(p[i:i + 1], 8, axis=0), tors) for i in range(n)])
+    return p, tors, pts
+
+
+def test_emulated_pairing_torsion_check(built, oracle):
+    """The pairing-based is_torsion_free (csrc/torsion.cuh, host emulation of the same source) gives the reference's
+    answer, [r]P == O (src/lib.rs:709-711), on every coset of the 8-torsion, on the small-order points themselves,
+    on the identity in several projective forms and on random full-order points."""
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libjj_emul.so"))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def flags(p):
+        p = np.ascontiguousarray(p)
+        out = np.zeros(len(p), np.uint8)
+        lib.emul_is_torsion_free(P(p), P(out), C.c_size_t(len(p)))
+        return out
+
+    prime, tors, cosets = _torsion_cosets(oracle, 24, 4242)
+    want = oracle.is_torsion_free(cosets)
+    assert want.reshape(-1, 8).sum(axis=1).tolist() == [1] * 24   # exactly one coset of each point is torsion free
+    assert (flags(cosets) == want).all()
+    assert (flags(prime) == 1).all()
+    assert (flags(tors) == oracle.is_torsion_free(tors)).all() and flags(tors).sum() == 1
+    # doubling changes the projective representation (z != 1, t1 * t2 != u * v / z form): flags are unchanged
+    d = oracle.ext_double(cosets)
+    assert (flags(d) == oracle.is_torsion_free(d)).all()
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 99, 64))
+    full = oracle.scalar_mul(np.repeat(g, 64, axis=0), t)
+    assert (flags(full) == oracle.is_torsion_free(full)).all()
+    # the identity and the point of order two (0, -1) in scaled projective forms (0, z, z, ..) / (0, -z, z, ..): U = 0
+    z = oracle.fe_stream(FQ, 7, 3)
+    ident = oracle.identity(3)
+    ident[:, 4:8], ident[:, 8:12], ident[:, 16:20] = z, z, z
+    assert (oracle.is_torsion_free(ident) == 1).all() and (flags(ident) == 1).all()
+    two = ident.copy()
+    two[:, 4:8] = oracle.fe_batch(FQ, oracle.OP_NEG, z)
+    assert (oracle.is_torsion_free(two) == 0).all() and (flags(two) == 0).all()
+
+
+def test_build_records_the_validated_nvcc(built):
+    """The carry-chain arithmetic was validated (GPU fuzz wall) for one ptxas only: build() records the nvcc it used
+    and refuses any other; a library built by an unvalidated toolchain must not pass silently."""
+    import json
+
+    info = json.load(open(os.path.join(ROOT, "jubjub_b200", "build_info.json")))
+    assert info["nvcc"] == built.VALIDATED_NVCC, info
+    assert "-lineinfo" in info["flags"] and "arch=compute_100a,code=sm_100a" in info["flags"]
+
+
+def test_types_star_import_and_vartime_gate():
+    """`from jubjub_b200.types import *` works and the `*` operator on points is gated behind an explicit
+    acknowledgement that the batch kernels are variable-time (the reference's `*` is constant-time, src/lib.rs:12-17)."""
+    ns = {}
+    exec("from jubjub_b200.types import *", ns)
+    for name in ("Fq", "Fr", "ExtendedPoint", "batch_mul_vartime", "acknowledge_vartime"):
+        assert name in ns, name
+    import jubjub_b200.types as T
+
+    assert hasattr(T.ExtendedPoint, "mul_vartime") and hasattr(T.AffinePoint, "mul_vartime")
+    import jubjub_b200 as jj
+
+    for name in ("scalar_mul_vartime", "scalar_mul_fixed_vartime", "scalar_mul_encoded_vartime", "scalar_mul_sharded_vartime"):
+        assert hasattr(jj.Engine, name), name
+    assert not hasattr(jj.Engine, "scalar_mul")
