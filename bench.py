@@ -191,7 +191,7 @@ def run_reference(args, rank, emit=print):
 
     cores = os.cpu_count() or 1
     logn = workload_log2(args)
-    sample = int(os.environ.get("JJ_REF_SAMPLE", str(min(1 << logn, 2048 * cores))))
+    sample = int(os.environ.get("JJ_REF_SAMPLE", str(min(1 << logn, 4096 * cores))))
     g = ob.affine_to_extended(ob.generator())
     t = ob.fe_to_bytes(ob.FR, ob.fe_stream(ob.FR, M.SEED0 + 3, sample))
     pts = ob.scalar_mul(np.repeat(g, sample, axis=0), t, cores)
@@ -388,9 +388,9 @@ def main():
     kms = timed(eng, lambda: eng.scalar_mul_vartime(pts, k, out=out_all, flags=jj.JJ_ASYNC), args.steps)
     hbm_peak, peak_src = measured_peaks()
     achieved_gbs = BYTES_PER_UNIT * n / (kms * 1e-3) / 1e9
-    peak_sampler = ClockSampler(local, period_ms=20).start()
-    time.sleep(0.1)
-    imad_peak = max(eng.imad_peak() for _ in range(4))
+    peak_sampler = ClockSampler(local, period_ms=50).start()
+    time.sleep(0.5)  # nvidia-smi needs a moment to start sampling
+    imad_peak = max(eng.imad_peak() for _ in range(16))  # ~45 ms each: the clock samples below are taken under this load
     peak_clocks = peak_sampler.stop()
     achieved_imad = IMADS_PER_UNIT * n / (kms * 1e-3)
 

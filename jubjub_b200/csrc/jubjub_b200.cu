@@ -28,7 +28,7 @@ struct Id128 {  // ncclUniqueId, passed by value
 
 namespace {
 
-constexpr size_t kChunkUnits = 1u << 17;  // host-staging chunk (units)
+constexpr size_t kChunkUnits = 1u << 17;  // default host-staging chunk (units); staging buffers grow to the chunk in use
 constexpr int kStages = 2;
 
 struct Staging {
@@ -309,7 +309,7 @@ struct Out {
     size_t unit;
 };
 // Launch(stream, din[3], dout[2], count, staging_or_null) -> status
-// chunk_units (<= kChunkUnits): units per staged chunk of a host-pointer call.
+// chunk_units: units per staged chunk of a host-pointer call (the staging buffers grow to it).
 template <class Launch>
 int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const Out (&outs)[2], Launch launch,
                   size_t chunk_units = kChunkUnits) {
@@ -348,7 +348,7 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
         size_t out_off[2] = {0, 0};
         for (int k = 0; k < 3; k++) {
             if (!ins[k].unit) continue;
-            int32_t rc = ensure(c, &S.buf[k], &S.cap[k], kChunkUnits * ins[k].unit, false);
+            int32_t rc = ensure(c, &S.buf[k], &S.cap[k], chunk_units * ins[k].unit, false);
             if (rc) return rc;
             CU(c, cudaMemcpyAsync(S.buf[k], (const char*)ins[k].p + done * ins[k].unit, cnt * ins[k].unit,
                                   cudaMemcpyHostToDevice, S.stream));
@@ -358,7 +358,7 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
             size_t need = 0;
             for (int k = 0; k < 2; k++) {
                 out_off[k] = need;
-                need += (kChunkUnits * outs[k].unit + 255) & ~(size_t)255;
+                need += (chunk_units * outs[k].unit + 255) & ~(size_t)255;
             }
             int32_t rc = ensure(c, &S.buf[3], &S.cap[3], need, false);
             if (rc) return rc;
@@ -504,10 +504,11 @@ int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in
     SmulArgs a = smul_args(pts, in_affine, sc, dst, cnt, flags & JJ_SCALAR_MONT);
     if (peers) a.peers = *peers;
     if (unit == 160) return launch_smul(c, s, a, tbl, tcap);
+    // The fused epilogue measured 1 % SLOWER than the separate pass on one GPU (34.63 vs 34.29 ms per 2^20, bench_ops r02a:
+    // 75 776 Fermat inversions, one per resident thread, against 32 768 in k_batch_normalize), so it is used where it
+    // pays -- the fused all-gather, which then moves 32-byte encodings instead of 160-byte points -- or on request.
     const bool default_map = smul_variant(c).id == kDefaultVariant;
-    bool fused = !S && default_map && cnt >= 4 * smul_round(c);
-    if (c->smul_variant == kFusedNormOn) fused = !S;
-    if (c->smul_variant == kFusedNormOff) fused = false;
+    bool fused = c->smul_variant == kFusedNormOn && !S;
     if (peers && peers->n_peers > 0) {
         if (S || !default_map) return fail(c, JJ_ERR_INVALID_ARG, "fused gather of converted outputs needs the default mapping");
         fused = true;
@@ -522,7 +523,7 @@ int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in
     // extended results go to scratch, then one pass normalises (and encodes) into the caller's buffer
     char** tmp = S ? &S->buf[2] : &c->tmp;
     size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;
-    int32_t rc = ensure(c, tmp, tmpcap, std::max(cnt, S ? kChunkUnits : cnt) * 160, !S);
+    int32_t rc = ensure(c, tmp, tmpcap, cnt * 160, !S);
     if (rc) return rc;
     a.out = *tmp;
     rc = launch_smul(c, s, a, tbl, tcap);
@@ -531,10 +532,12 @@ int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in
     return normalize_launch(c, s, *tmp, dst, cnt, unit, tbl, tcap, !S);
 }
 // whole rounds per staged chunk: a chunk that ends in a partly filled round leaves the multiplier pipe
-// under-occupied for that round
-size_t smul_chunk(const jj_ctx* c) {
+// under-occupied for that round.  `rounds` = 1 keeps the exposed first upload / last download small (the 352 B/unit
+// ExtendedPoint path); the wire-format path moves 65 B/unit and wants chunks of several rounds instead, so that the
+// decode kernel's threads amortise their Fermat inversion over a chain of encodings.
+size_t smul_chunk(const jj_ctx* c, int rounds = 1) {
     const size_t round = smul_round(c);
-    return round && round <= kChunkUnits ? kChunkUnits / round * round : kChunkUnits;
+    return round ? round * rounds : kChunkUnits;
 }
 
 // fixed-base window width: 7 (216 KB table, the default) or 4 (47 KB table, variant 100)
@@ -977,7 +980,7 @@ int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scala
         // decode -> AffinePoint scratch (64 B) [-> subgroup test on it] -> scalar-mul reading the affine points directly
         char** aff = S ? &S->tmp2 : &c->tmp2;
         size_t* affcap = S ? &S->tmp2_cap : &c->tmp2_cap;
-        int32_t rc = ensure(c, aff, affcap, std::max(cnt, S ? kChunkUnits : cnt) * 64, !S);
+        int32_t rc = ensure(c, aff, affcap, cnt * 64, !S);
         if (rc) return rc;
         rc = from_bytes_launch(c, s, din[0], *aff, (uint8_t*)dout[1], cnt, zip216);
         if (rc) return rc;
@@ -987,7 +990,7 @@ int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scala
             CU(c, cudaGetLastError());
         }
         return smul_any(c, s, S, *aff, true, din[1], dout[0], cnt, flags);
-    }, smul_chunk(c));
+    }, smul_chunk(c, 4));
 }
 
 int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scalars, void* out, size_t n, uint32_t flags) {
@@ -1006,7 +1009,7 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
         char** tmp = S ? &S->buf[2] : &c->tmp;
         size_t* tmpcap = S ? &S->cap[2] : &c->tmp_cap;
         if (unit != 160) {
-            int32_t rc = ensure(c, tmp, tmpcap, std::max(cnt, S ? kChunkUnits : cnt) * 160, !S);
+            int32_t rc = ensure(c, tmp, tmpcap, cnt * 160, !S);
             if (rc) return rc;
             dst = *tmp;
         }
@@ -1229,8 +1232,8 @@ int32_t jj_scalar_mul_sharded_n(jj_ctx* c, const void* points_local, const void*
                 CU(c, cudaStreamWaitEvent(S.stream, c->ev_fork, 0));
                 used++;
             }
-            int32_t rc = ensure(c, &S.buf[0], &S.cap[0], kChunkUnits * 160, false);
-            if (!rc) rc = ensure(c, &S.buf[1], &S.cap[1], kChunkUnits * 32, false);
+            int32_t rc = ensure(c, &S.buf[0], &S.cap[0], chunk * 160, false);
+            if (!rc) rc = ensure(c, &S.buf[1], &S.cap[1], chunk * 32, false);
             if (rc) return rc;
             CU(c, cudaMemcpyAsync(S.buf[0], (const char*)points_local + done * 160, cnt * 160, cudaMemcpyHostToDevice, S.stream));
             CU(c, cudaMemcpyAsync(S.buf[1], (const char*)scalars_local + done * 32, cnt * 32, cudaMemcpyHostToDevice, S.stream));

@@ -8,7 +8,7 @@ if [ "$N" = "2" ]; then
   echo "pytest multi rc=$?" | tee -a gpurun_out/${tag}_pytest_gpu_multi_n2.txt; tail -4 gpurun_out/${tag}_pytest_gpu_multi_n2.txt
 fi
 export JJ_CPU_SAMPLE=${JJ_CPU_SAMPLE:-32768}
-export NCCL_DEBUG=${NCCL_DEBUG:-INFO}
+export NCCL_DEBUG=INFO
 run() { # name, extra env
   env $2 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $3 \
     bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 > gpurun_out/${tag}_bench_n${N}_$1.json 2> gpurun_out/${tag}_bench_n${N}_$1.err

@@ -498,7 +498,7 @@ def test_scalar_mul_encoded_subgroup_check(eng, oracle):
     _, dec_ok = eng.batch_from_bytes(enc)
     want_ok = dec_ok & ((t[:, 0] & 7) == 0)
     got, ok = eng.scalar_mul_encoded_vartime(enc, k, check_subgroup=True)
-    assert (ok == want_ok).all() and 0.25 * n < ok.sum() < 0.4 * n
+    assert (ok == want_ok).all() and 0.35 * n < ok.sum() < 0.45 * n  # 1/3 forced + 1/8 of the rest, minus undecodable
     plain, _ = eng.scalar_mul_encoded_vartime(enc, k)
     assert (got[ok == 1] == plain[ok == 1]).all()
     s = np.flatnonzero(ok)[:300]
