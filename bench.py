@@ -260,9 +260,10 @@ def main():
     os.dup2(2, 1)
 
     def emit(line):
+        # written straight to the saved descriptor: fd 1 stays pointed at stderr, so whatever NCCL logs while the
+        # process group is torn down cannot land after the JSON line
         sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        print(line, flush=True)
+        os.write(real_stdout, (line + "\n").encode())
 
     if args.impl == "reference":
         run_reference(args, rank, emit)

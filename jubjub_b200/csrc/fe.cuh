@@ -228,6 +228,21 @@ template <class F>
 JJ_DEVICE void fe_dbl(fe& r, const fe& a) {
     fe_add<F>(r, a, a);
 }
+// a + b WITHOUT the final reduction: the sum of two canonical values lies in [0, 2m) and 2m < 2^256 for both fields,
+// so it still fits 8 limbs.  Such a "lazy" value may only be used where any 256-bit integer is allowed: as the SECOND
+// operand of mont_mul (its precondition, and what from_raw relies on) or as the minuend of fe_sub, whose add-back then
+// lands in [0, 2m) again.  Saves the 8 trial subtractions + 8 selects (+ borrow) of fe_reduce_once; every value that
+// leaves a point formula is still the fully reduced representative.
+template <class F>
+JJ_DEVICE void fe_add_lazy(fe& r, const fe& a, const fe& b) {
+    uint32_t s[8];
+    add_cc(s[0], a.w[0], b.w[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(s[i], a.w[i], b.w[i]);
+    addc(s[7], a.w[7], b.w[7]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.w[i] = s[i];
+}
 template <class F>
 JJ_DEVICE void fe_sub(fe& r, const fe& a, const fe& b) {
     uint32_t d[8], mask;

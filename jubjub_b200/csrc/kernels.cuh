@@ -342,6 +342,10 @@ struct SmemTable {
     __device__ __forceinline__ void load(int j, ext_niels& n) const {
         get(j * 4, n.vpu); get(j * 4 + 1, n.vmu); get(j * 4 + 2, n.z); get(j * 4 + 3, n.t2d);
     }
+    __device__ __forceinline__ void load_signed(int j, bool neg, ext_niels& n) const {
+        const int o = neg ? 1 : 0;
+        get(j * 4 + o, n.vpu); get(j * 4 + 1 - o, n.vmu); get(j * 4 + 2, n.z); get(j * 4 + 3, n.t2d);
+    }
 };
 #endif
 // Window table in global scratch (L2-resident: resident threads x 1 KB), laid out
@@ -356,6 +360,12 @@ struct GmemTable {
     __device__ __forceinline__ void load(int j, ext_niels& n) const {
         const char* p = base + (size_t)j * 4 * 1024;
         ld_fe_keep(n.vpu, p); ld_fe_keep(n.vmu, p + 1024); ld_fe_keep(n.z, p + 2048); ld_fe_keep(n.t2d, p + 3072);
+    }
+    // entry j with its v+u / v-u halves exchanged by address when neg (scalarmul.cuh: LocalTable::load_signed)
+    __device__ __forceinline__ void load_signed(int j, bool neg, ext_niels& n) const {
+        const char* p = base + (size_t)j * 4 * 1024;
+        const int o = neg ? 1024 : 0;
+        ld_fe_keep(n.vpu, p + o); ld_fe_keep(n.vmu, p + 1024 - o); ld_fe_keep(n.z, p + 2048); ld_fe_keep(n.t2d, p + 3072);
     }
 };
 

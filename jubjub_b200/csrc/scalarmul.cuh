@@ -43,10 +43,19 @@ JJ_DEVICE void shl_256(uint32_t K[8], int s) {  // 0 < s < 32
 }
 
 // Table policy used by the host emulation and as the plain fallback layout: a private array.
+// load_signed(j, neg, n): entry j with its v+u / v-u halves exchanged when neg -- i.e. the Niels form of -(j+1)P up to
+// the sign of t2d, which the addition's output side handles (point_add_niels_preswapped).
 struct LocalTable {
     ext_niels t[8];
     JJ_DEVICE_SPEC void store(int j, const ext_niels& n) { t[j] = n; }
     JJ_DEVICE_SPEC void load(int j, ext_niels& n) const { n = t[j]; }
+    JJ_DEVICE_SPEC void load_signed(int j, bool neg, ext_niels& n) const {
+        n = t[j];
+        if (neg) {
+            n.vpu = t[j].vmu;
+            n.vmu = t[j].vpu;
+        }
+    }
 };
 
 #ifndef JJ_DBL_UNROLL
@@ -91,8 +100,8 @@ JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_
         shl_256(K, 4);
         if (d != 0) {
             ext_niels n;
-            tbl.load((d < 0 ? -d : d) - 1, n);
-            point_add_niels(acc, acc, n, d < 0);
+            tbl.load_signed((d < 0 ? -d : d) - 1, d < 0, n);
+            point_add_niels_preswapped(acc, acc, n, d < 0);
         }
     }
 }
@@ -167,8 +176,8 @@ JJ_DEVICE void scalar_mul_wnaf_core(ext_point& acc, const ext_point& P, const Na
         const int d = naf.d[i];
         if (d != 0) {
             ext_niels n;
-            tbl.load(((d < 0 ? -d : d) - 1) >> 1, n);
-            point_add_niels(acc, acc, n, d < 0);
+            tbl.load_signed(((d < 0 ? -d : d) - 1) >> 1, d < 0, n);
+            point_add_niels_preswapped(acc, acc, n, d < 0);
         }
     }
 }
@@ -194,6 +203,17 @@ struct fixed_table_view {
         for (int w = 0; w < 8; w++) {
             n.vpu.w[w] = p[w];
             n.vmu.w[w] = p[8 + w];
+            n.t2d.w[w] = p[16 + w];
+        }
+    }
+    // halves exchanged by address for a negative digit (see LocalTable::load_signed)
+    JJ_DEVICE_SPEC void load_signed(int entry, bool neg, aff_niels& n) const {
+        const uint32_t* p = base + entry * 24;
+        const int o = neg ? 8 : 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            n.vpu.w[w] = p[o + w];
+            n.vmu.w[w] = p[8 - o + w];
             n.t2d.w[w] = p[16 + w];
         }
     }
@@ -228,8 +248,8 @@ JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const 
         t[7] >>= W;
         if (d != 0) {
             aff_niels n;
-            tbl.load(i * PER + (d < 0 ? -d : d) - 1, n);
-            point_add_aff_niels_t<INL>(acc, acc, n, d < 0);  // <INL, false> (112-multiply rows) measures the same
+            tbl.load_signed(i * PER + (d < 0 ? -d : d) - 1, d < 0, n);
+            point_add_aff_niels_t<INL, kM1MulDefault, true>(acc, acc, n, d < 0);  // <INL, false> (112-multiply rows) measures the same
         }
     }
 }
