@@ -135,14 +135,14 @@ def oracle_expected(first, count, threads):
     return ob.batch_normalize(ob.scalar_mul(pts, k, threads))
 
 
-def parity_check(eng, out_all, n, world, rank, dist, threads, sample_per_block=1024, runs=8):
+def parity_check(eng, out_all, n, world, rank, dist, threads, sample_per_block=1024, runs=8, fmt="extended"):
     """Every rank: (1) a digest of its whole gathered buffer, compared across ranks; (2) `sample_per_block` units of
     EVERY rank's block (runs of consecutive indices at fixed pseudo-random offsets) recomputed by the oracle from the
     input streams by global index -- a misplaced block or a stale buffer fails this, not only a wrong value."""
     from oracle import binding as ob
 
-    host = out_all.download()  # (world * n, 20)
-    words = host.reshape(-1)
+    host = out_all.download()  # (world * n, 20) uint64, or (world * n, 32) uint8 encodings
+    words = host.reshape(-1).view(np.uint64)
     s1 = s2 = np.uint64(0)
     step = 1 << 24
     with np.errstate(over="ignore"):
@@ -159,7 +159,10 @@ def parity_check(eng, out_all, n, world, rank, dist, threads, sample_per_block=1
         for s in rng.randint(0, n - run_len, size=runs):
             first = r * n + int(s)
             want = oracle_expected(first, run_len, threads)
-            got = ob.batch_normalize(host[first:first + run_len])
+            if fmt == "bytes":
+                got, want = host[first:first + run_len], ob.affine_to_bytes(want)
+            else:
+                got = ob.batch_normalize(host[first:first + run_len])
             bad += int((got != want).any(axis=1).sum())
             checked += run_len
     digests = [digest]
@@ -283,8 +286,11 @@ def main():
     logn = workload_log2(args)
     n = 1 << logn
     pts, k = make_inputs(eng, n, first=rank * n)
-    unit_out = 160
-    out_all = eng.empty((world * n, 20))
+    # JJ_OUT=bytes (information only, N > 1): every rank gathers the 32-byte encodings of the results instead of the
+    # 160-byte points -- the kernel's fused normalise epilogue + 32-byte P2P stores.  The headline stays ExtendedPoint.
+    out_fmt = os.environ.get("JJ_OUT", "extended") if world > 1 else "extended"
+    unit_out = 160 if out_fmt == "extended" else 32
+    out_all = eng.empty((world * n, 20)) if out_fmt == "extended" else eng.empty((world * n, 32), np.uint8)
     gather = "none"
     if world > 1:
         ids = [eng.comm_unique_id() if rank == 0 else None]
@@ -309,7 +315,7 @@ def main():
 
     def step():
         if world > 1:
-            eng.scalar_mul_sharded_vartime(pts, k, out_all, async_=True)
+            eng.scalar_mul_sharded_vartime(pts, k, out_all, output=out_fmt, async_=True)
         else:
             eng.scalar_mul_vartime(pts, k, out=out_all, flags=jj.JJ_ASYNC)
 
@@ -344,20 +350,20 @@ def main():
     # ---- parity of what was just timed: every rank checks the gathered buffer the last step left behind
     cores = os.cpu_count() or 1
     threads = max(1, cores // world)
-    parity = parity_check(eng, out_all, n, world, rank, dist, threads)
+    parity = parity_check(eng, out_all, n, world, rank, dist, threads, fmt=out_fmt)
 
     # ---- e2e: HOST (pinned) inputs through the C ABI, results on every rank, own block read back to the host;
     # H2D, kernels, gather and D2H all inside the timed region
     hp, hp_ptr = pinned(eng, (n, 20), np.uint64)
     hk, hk_ptr = pinned(eng, (n, 32), np.uint8)
-    ho, ho_ptr = pinned(eng, (n, 20), np.uint64)
+    ho, ho_ptr = pinned(eng, (n, 20), np.uint64) if out_fmt == "extended" else pinned(eng, (n, 32), np.uint8)
     hp[:] = pts.download()
     hk[:] = k.download()
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
         if world > 1:
-            eng.scalar_mul_sharded_vartime(hp, hk, out_all, out_local_host=ho)
+            eng.scalar_mul_sharded_vartime(hp, hk, out_all, output=out_fmt, out_local_host=ho)
         else:
             eng.scalar_mul_vartime(hp, hk, out=ho)
 
@@ -386,6 +392,8 @@ def main():
 
     # ---- rank 0 only from here: kernel-only duration of the dominant kernel (same launches, no gather), for the roofline
     eng.set_peer_outputs(None)
+    if out_fmt != "extended":
+        out_all = eng.empty((n, 20))
     kms = timed(eng, lambda: eng.scalar_mul_vartime(pts, k, out=out_all, flags=jj.JJ_ASYNC), args.steps)
     hbm_peak, peak_src = measured_peaks()
     achieved_gbs = BYTES_PER_UNIT * n / (kms * 1e-3) / 1e9
@@ -432,7 +440,7 @@ def main():
     enc_dev = eng.affine_to_bytes(eng.batch_normalize(pts))
     henc, henc_ptr = pinned(eng, (n, 32), np.uint8)
     hout, hout_ptr = pinned(eng, (n, 32), np.uint8)
-    hok = np.zeros((n,), np.uint8)
+    hok, hok_ptr = pinned(eng, (n,), np.uint8)  # pageable memory here would serialise the staged chunks
     henc[:] = enc_dev.download()
 
     def wire_step():
@@ -484,7 +492,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (8x32-bit Montgomery, IMAD.WIDE.U32)", "data": "synthetic",
         "config": {"workload": workload_name(world, logn), "units_per_gpu": n, "total_units": world * n,
-                   "output": "ExtendedPoint (160 B)", "collective": collective,
+                   "output": "ExtendedPoint (160 B)" if out_fmt == "extended" else "32-byte encodings (normalise + encode fused into the kernel)",
+                   "collective": collective,
                    "cache": f"inputs+outputs {352 * n / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed); kernel is integer-bound"},
         "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * n * 192,
                 "d2h_bytes_per_step": world * n * unit_out, "ms_per_step": e2e_s * 1e3,

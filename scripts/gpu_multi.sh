@@ -19,7 +19,8 @@ run() { # name, extra env
 }
 run p2p "JJ_GATHER=p2p" 29517
 [ -n "$SKIP_NCCL" ] || run nccl "JJ_GATHER=nccl" 29518
-for f in gpurun_out/${tag}_bench_n${N}_p2p.json gpurun_out/${tag}_bench_n${N}_nccl.json; do [ -s "$f" ] || continue
+[ -z "$WITH_BYTES" ] || run p2p_bytes "JJ_GATHER=p2p JJ_OUT=bytes" 29519
+for f in gpurun_out/${tag}_bench_n${N}_p2p.json gpurun_out/${tag}_bench_n${N}_nccl.json gpurun_out/${tag}_bench_n${N}_p2p_bytes.json; do [ -s "$f" ] || continue
 python - "$f" <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
