@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -540,6 +541,22 @@ size_t smul_chunk(const jj_ctx* c, int rounds = 1) {
     return round ? round * rounds : kChunkUnits;
 }
 
+// Rounds per staged chunk of the wire-format path.  Measured per 2^20 units (pinned host buffers, scripts/wire_sweep.py):
+// 1 round 47.1 ms, 2: 43.5, 4: 41.8, 6: 41.4, 8: 40.8, 14 (one chunk): 41.2 -- against 39.5 ms device-resident.  Eight rounds
+// give the decode kernel chains of 8 encodings per thread (its device-resident efficiency).  A smaller first chunk (to shorten
+// the one upload nothing overlaps) was measured and does not pay: 40.9 (none) / 40.9 (1 round) / 41.1 (2) / 41.4 ms (4).
+// JJ_WIRE_ROUNDS overrides (experiments).
+int env_rounds(const char* name, int dflt) {
+    const char* e = getenv(name);
+    int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 64 ? v : dflt;
+}
+int wire_rounds() {
+    static const int r = env_rounds("JJ_WIRE_ROUNDS", 8);
+    return r;
+}
+
+
 // fixed-base window width: 7 (216 KB table, the default) or 4 (47 KB table, variant 100)
 int fixed_w(const jj_ctx* c) { return c->smul_variant == kFixedW4 ? 4 : 7; }
 
@@ -990,7 +1007,7 @@ int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scala
             CU(c, cudaGetLastError());
         }
         return smul_any(c, s, S, *aff, true, din[1], dout[0], cnt, flags);
-    }, smul_chunk(c, 4));
+    }, smul_chunk(c, wire_rounds()));
 }
 
 int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scalars, void* out, size_t n, uint32_t flags) {
