@@ -83,8 +83,9 @@ const char* jj_last_error(const jj_ctx* ctx);
 const char* jj_version(void);
 int32_t jj_device_info(jj_ctx* ctx, int32_t* sm_count, int32_t* sm_clock_khz, uint64_t* hbm_bytes);
 /* Tuning knob; 0 = library defaults.  13 / 24 / 5: variable-base kernel with 16 / 24 / 8 warps
- * per SM; 100: fixed-base kernel with 4-bit windows; 200 / 201: converted outputs of device-resident variable-base
- * batches always / never use the kernel's fused normalise epilogue (default: from 4 rounds of resident threads up). */
+ * per SM; 100: fixed-base kernel with 4-bit windows; 200 / 201: converted outputs (JJ_OUT_AFFINE / JJ_OUT_BYTES) of
+ * device-resident variable-base batches always / never use the kernel's fused normalise epilogue (default: only for the
+ * fused all-gather, where it shrinks the peer stores to 32 bytes; on one GPU the separate pass is 1 % faster). */
 int32_t jj_set_scalar_mul_variant(jj_ctx* ctx, int32_t variant);
 /* Number of this library's kernel launches issued on ctx so far (bench.py's gpu_launches). */
 uint64_t jj_launch_count(const jj_ctx* ctx);
