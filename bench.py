@@ -399,7 +399,7 @@ def main():
     achieved_gbs = BYTES_PER_UNIT * n / (kms * 1e-3) / 1e9
     peak_sampler = ClockSampler(local, period_ms=50).start()
     time.sleep(0.5)  # nvidia-smi needs a moment to start sampling
-    imad_peak = max(eng.imad_peak() for _ in range(16))  # ~45 ms each: the clock samples below are taken under this load
+    imad_peak = max(eng.imad_peak() for _ in range(6))  # ~150 ms each: the clock samples below are taken under this load
     peak_clocks = peak_sampler.stop()
     achieved_imad = IMADS_PER_UNIT * n / (kms * 1e-3)
 
@@ -509,8 +509,10 @@ def main():
                      "peak": imad_peak / 1e12, "unit": "T thread-ops/s of IMAD.WIDE.U32", "frac": achieved_imad / imad_peak,
                      "imads_per_unit_algorithmic": IMADS_PER_UNIT, "imads_issued_per_unit": NCU_IMADS_ISSUED_PER_UNIT,
                      "frac_issued": NCU_IMADS_ISSUED_PER_UNIT * n / (kms * 1e-3) / imad_peak,
-                     "peak_source": "measured live by jj_measure_imad_peak (register-only IMAD.WIDE.U32 chains, best of 4); "
-                                    "not in MEASURED_PEAKS.json", "peak_clocks": peak_clocks,
+                     "peak_source": "measured live by jj_measure_imad_peak: best of three register-only probes (IMAD.WIDE.U32 chains "
+                                    "with register operands / with an immediate multiplier at 64 warps/SM, dependent Fq-product "
+                                    "chains at 16 warps/SM), best of 6 calls; not in MEASURED_PEAKS.json; nominal 32 lanes/clk/SM x "
+                                    "148 x 1.965 GHz = 9.31", "peak_clocks": peak_clocks,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_PROFILE,
                      "kernel": "k_scalar_mul<512,1,GMEM>", "kernel_ms": kms},
         "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -116,8 +116,9 @@ int32_t jj_graph_begin(jj_ctx* ctx);
 int32_t jj_graph_end(jj_ctx* ctx, void** graph_exec);
 int32_t jj_graph_launch(jj_ctx* ctx, void* graph_exec);
 int32_t jj_graph_destroy(jj_ctx* ctx, void* graph_exec);
-/* Measures the chip's IMAD.WIDE.U32 issue rate (instructions x 32 lanes per second) with a
- * register-only kernel: the integer-pipe roofline denominator. */
+/* Measures the chip's IMAD.WIDE.U32 issue rate (instructions x 32 lanes per second) with register-only kernels -- the best
+ * of three probes (accumulate chains with register operands, with an immediate multiplier, and dependent chains of whole
+ * Fq products): the integer-pipe roofline denominator. */
 int32_t jj_measure_imad_peak(jj_ctx* ctx, double* imad_per_sec);
 
 /* ---- field batches: out[i] = a[i] (op) b[i]; field = Fq (jj_fq_*) or Fr (jj_fr_*) --------- */

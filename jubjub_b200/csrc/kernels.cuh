@@ -811,11 +811,34 @@ __global__ void k_fq_sqrt_init(uint32_t* status) {
     if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = fq_sqrt_tables_build(g_fq_sqrt_tab) ? 1u : 0u;
 }
 
-// Integer-multiplier peak probe: register-only, 8 independent accumulate chains per thread of
-// IMAD.WIDE.U32 (32x32+64 -> 64), the instruction the Montgomery kernels are made of and the
-// unit the scalar-mul roofline is counted in.  The multiplicand is the
-// chain's own previous low word, so ptxas cannot hoist or strength-reduce the products.
+// Integer-multiplier peak probes: register-only IMAD.WIDE.U32 (32x32+64 -> 64), the instruction the Montgomery kernels are
+// made of and the unit the scalar-mul roofline is counted in.  The multiplicand is the chain's own
+// previous low word, so ptxas cannot hoist or strength-reduce the products.
+//   MODE 0: 8 independent accumulate chains per thread, all-register operands
+//   MODE 1: the same with an immediate multiplier (the form of the reduction rows): one register read fewer per instruction
+//   MODE 2: dependent chains of whole Fq products (119 IMAD.WIDE + ~50 other instructions each) -- the densest multiplier
+//           stream the engine's own code can issue; measured the highest of the three (8.74e12 /s against 8.53e12 / 8.67e12)
+// jj_measure_imad_peak reports the best of the three: the roofline denominator is what the chip was SEEN to sustain.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, uint32_t seed, int iters) {
+    if (MODE == 2) {
+        fe a, b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            a.w[i] = (seed + threadIdx.x * 977u + i * 31u) & 0x3fffffffu;
+            b.w[i] = (seed * 3u + blockIdx.x * 131u + i * 17u) & 0x3fffffffu;
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+            mont_mul<FqP, true>(a, a, b);
+            mont_mul<FqP, true>(b, b, a);
+        }
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) x ^= a.w[i] ^ b.w[i];
+        if (x == 0x1234567u) sink[0] = x;
+        return;
+    }
     uint32_t lo[8], hi[8];
     const uint32_t a = seed * 2654435761u + threadIdx.x * 40503u + blockIdx.x;
 #pragma unroll
@@ -830,8 +853,13 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, uint32_t seed
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 uint32_t m = lo[k];
-                mad_lo_cc(lo[k], a, m, lo[k]);
-                madc_hi(hi[k], a, m, hi[k]);
+                if (MODE == 0) {
+                    mad_lo_cc(lo[k], a, m, lo[k]);
+                    madc_hi(hi[k], a, m, hi[k]);
+                } else {
+                    JJ_MAD_LO_CC_I(lo[k], m, 0x53bda402, lo[k]);
+                    JJ_MADC_HI_I(hi[k], m, 0x53bda402, hi[k]);
+                }
             }
         }
     }
@@ -840,6 +868,9 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, uint32_t seed
     for (int k = 0; k < 8; k++) x ^= lo[k] ^ hi[k];
     if (x == 0x1234567u) sink[0] = x;  // keeps the chains alive
 }
+// IMAD.WIDE instructions per product of MODE 2 (checked against the SASS by scripts/sass_summary.py: the shared Fq
+// product body is 119 IMAD.WIDE)
+constexpr int kImadWidePerFqMul = 119;
 
 // Writes a buffer larger than L2 (bench.py's flush between timed iterations).
 __global__ void k_fill(uint4* p, size_t n16, uint32_t v) {
