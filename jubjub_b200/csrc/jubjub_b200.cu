@@ -1249,7 +1249,8 @@ int32_t jj_scalar_mul_sharded_n(jj_ctx* c, const void* points_local, const void*
         // k+1 overlaps the kernel of chunk k); every chunk's kernel writes its results into place -- all ranks' buffers
         // when fused -- and the chunk is read back to the host from this rank's own copy.
         CU(c, cudaEventRecord(c->ev_fork, c->stream));
-        const size_t chunk = smul_chunk(c);
+        static const int shard_rounds = env_rounds("JJ_SHARD_ROUNDS", 1);  // experiments: rounds per staged chunk
+        const size_t chunk = smul_chunk(c, shard_rounds);
         size_t done = 0;
         int stage = 0, used = 0;
         while (done < n_local) {
