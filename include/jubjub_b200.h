@@ -34,8 +34,9 @@
  * src/fr.rs:539; non-canonical bytes, src/fr.rs:291; off-curve encodings, src/lib.rs:492-534)
  * are reported in a `uint8_t ok[n]` side array, not as an error.
  *
- * The batch entry points are variable-time in their data; the reference's constant-time
- * policy (src/lib.rs:12-17) is kept by its scalar API, not by this batch engine.
+ * The batch entry points are variable-time in their data (the reference's constant-time policy is src/lib.rs:12-17).
+ * The variable-base scalar multiplication has a constant-time-in-the-scalar mode, JJ_CONST_TIME; everything else
+ * (fixed-base tables, decoding, inversion chains) is for public data.
  */
 #ifndef JUBJUB_B200_H
 #define JUBJUB_B200_H
@@ -71,8 +72,12 @@ enum {
     JJ_PRE_ZIP216 = 1u << 7, /* jj_batch_from_bytes: from_bytes_pre_zip216_compatibility (src/lib.rs:485-490) */
     JJ_CHECK_SUBGROUP = 1u << 8, /* jj_scalar_mul_encoded: ok[i] also requires is_torsion_free, i.e. the decode is
                                     SubgroupPoint::from_bytes (src/lib.rs:1427-1429) */
-    JJ_TORSION_LADDER = 1u << 9  /* jj_is_torsion_free: decide by the reference's own [r]P == O (src/lib.rs:709-711)
+    JJ_TORSION_LADDER = 1u << 9, /* jj_is_torsion_free: decide by the reference's own [r]P == O (src/lib.rs:709-711)
                                     instead of the pairing test -- same flags, ~7x the work; the cross-check */
+    JJ_CONST_TIME = 1u << 10     /* jj_scalar_mul / jj_scalar_mul_encoded / jj_scalar_mul_sharded*: no branch and no memory
+                                    address depends on the SCALAR (window table scanned, sign by selects, every addition
+                                    executed -- the batch analogue of the reference's "always add P or identity",
+                                    src/lib.rs:356-379).  Same results, slower kernel; points are treated as public. */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */

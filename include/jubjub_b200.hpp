@@ -73,6 +73,13 @@ class Engine {
         check(jj_scalar_mul(ctx_, p.data(), k.data(), out.data(), p.size(), JJ_SCALAR_MONT));
         return out;
     }
+    // the same in the engine's constant-time-in-the-scalar mode (JJ_CONST_TIME): no branch or address depends on k
+    std::vector<ExtendedPoint> batch_mul(const std::vector<ExtendedPoint>& p, const std::vector<Fr>& k) {
+        same(p.size(), k.size());
+        std::vector<ExtendedPoint> out(p.size());
+        check(jj_scalar_mul(ctx_, p.data(), k.data(), out.data(), p.size(), JJ_SCALAR_MONT | JJ_CONST_TIME));
+        return out;
+    }
     // `&AffinePoint * &Fr` for one shared base (src/lib.rs:1109-1115)
     std::vector<ExtendedPoint> batch_mul_fixed_vartime(const AffinePoint& base, const std::vector<Fr>& k) {
         std::vector<ExtendedPoint> out(k.size());

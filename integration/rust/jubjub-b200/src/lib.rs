@@ -55,6 +55,7 @@ pub const JJ_OUT_BYTES: u32 = 1 << 6;
 pub const JJ_PRE_ZIP216: u32 = 1 << 7;
 pub const JJ_CHECK_SUBGROUP: u32 = 1 << 8;
 pub const JJ_TORSION_LADDER: u32 = 1 << 9;
+pub const JJ_CONST_TIME: u32 = 1 << 10;
 
 #[link(name = "jubjub_b200")]
 extern "C" {

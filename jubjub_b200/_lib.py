@@ -23,6 +23,7 @@ JJ_OUT_BYTES = 1 << 6
 JJ_PRE_ZIP216 = 1 << 7
 JJ_CHECK_SUBGROUP = 1 << 8
 JJ_TORSION_LADDER = 1 << 9
+JJ_CONST_TIME = 1 << 10
 
 ERRORS = {0: "JJ_OK", -1: "JJ_ERR_INVALID_ARG", -2: "JJ_ERR_CUDA", -3: "JJ_ERR_NCCL", -4: "JJ_ERR_OOM",
           -5: "JJ_ERR_NO_DEVICE"}

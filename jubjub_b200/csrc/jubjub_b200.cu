@@ -209,9 +209,9 @@ size_t smul_round(const jj_ctx* c) {
     return (size_t)c->sm_count * v.threads * v.min_blocks;
 }
 
-template <int T, int MB, int TAB, bool NORM>
+template <int T, int MB, int TAB, bool NORM, bool CT = false>
 int32_t launch_smul_t(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
-    auto kern = k_scalar_mul<T, MB, TAB, NORM>;
+    auto kern = k_scalar_mul<T, MB, TAB, NORM, CT>;
     size_t smem = TAB == TABLE_SMEM ? (size_t)(T / 32) * 32768 : 0;
     int grid = grid_for(c, a.n, T, MB);
     if (TAB == TABLE_SMEM) {
@@ -245,8 +245,13 @@ int32_t launch_smul_slots(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, siz
 // a.out_unit = 160: ExtendedPoint results.  64 / 32: the fused normalise epilogue (default mapping only); the caller
 // provides a.norm_scratch (norm_scratch_bytes()).
 size_t norm_scratch_bytes(const jj_ctx* c, size_t n) { return n * 128 + smul_round(c) * 32; }
-int32_t launch_smul(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap) {
+int32_t launch_smul(jj_ctx* c, cudaStream_t s, SmulArgs a, char** tbl, size_t* tbl_cap, bool const_time = false) {
     const SmulVariant& v = smul_variant(c);
+    if (const_time) {
+        if (a.out_unit != 160 || v.id != kDefaultVariant)
+            return fail(c, JJ_ERR_INVALID_ARG, "JJ_CONST_TIME runs the default mapping with ExtendedPoint results (convert afterwards)");
+        return launch_smul_t<512, 1, TABLE_GMEM, false, true>(c, s, a, tbl, tbl_cap);
+    }
     if (a.out_unit != 160) {
         if (v.id != kDefaultVariant) return fail(c, JJ_ERR_INVALID_ARG, "the fused normalise epilogue exists for the default mapping only");
         return launch_smul_t<512, 1, TABLE_GMEM, true>(c, s, a, tbl, tbl_cap);
@@ -502,16 +507,19 @@ int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in
     char** tbl = S ? &S->tbl : &c->tbl;
     size_t* tcap = S ? &S->tbl_cap : &c->tbl_cap;
     const int unit = (int)out_unit(flags);
+    const bool ct = flags & JJ_CONST_TIME;
     SmulArgs a = smul_args(pts, in_affine, sc, dst, cnt, flags & JJ_SCALAR_MONT);
     if (peers) a.peers = *peers;
-    if (unit == 160) return launch_smul(c, s, a, tbl, tcap);
+    if (unit == 160) return launch_smul(c, s, a, tbl, tcap, ct);
     // The fused epilogue measured 1 % SLOWER than the separate pass on one GPU (34.63 vs 34.29 ms per 2^20, bench_ops r02a:
     // 75 776 Fermat inversions, one per resident thread, against 32 768 in k_batch_normalize), so it is used where it
     // pays -- the fused all-gather, which then moves 32-byte encodings instead of 160-byte points -- or on request.
     const bool default_map = smul_variant(c).id == kDefaultVariant;
     bool fused = c->smul_variant == kFusedNormOn && !S;
+    if (ct) fused = false;  // constant-time mode: ExtendedPoint kernel, then the separate normalise pass
     if (peers && peers->n_peers > 0) {
-        if (S || !default_map) return fail(c, JJ_ERR_INVALID_ARG, "fused gather of converted outputs needs the default mapping");
+        if (S || !default_map || ct)
+            return fail(c, JJ_ERR_INVALID_ARG, "fused gather of converted outputs needs the default, variable-time mapping");
         fused = true;
     }
     if (fused) {
@@ -527,7 +535,7 @@ int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in
     int32_t rc = ensure(c, tmp, tmpcap, cnt * 160, !S);
     if (rc) return rc;
     a.out = *tmp;
-    rc = launch_smul(c, s, a, tbl, tcap);
+    rc = launch_smul(c, s, a, tbl, tcap, ct);
     if (rc) return rc;
     // the running products of the normalise pass for 32-byte outputs live in the (dead) scalar-mul table scratch
     return normalize_launch(c, s, *tmp, dst, cnt, unit, tbl, tcap, !S);

@@ -440,7 +440,8 @@ __device__ __forceinline__ void smul_store_norm(const SmulArgs& a, size_t i, con
 // the thread's own units, as ff::BatchInverter does along the slice; z = 0 is skipped and yields (0, 0)) and walks back.
 // The fused all-gather then moves 32-byte encodings instead of 160-byte points.  Worth it when a thread owns several
 // units (device-resident batches); host-staged chunks of one round use the separate k_batch_normalize pass.
-template <int THREADS, int MIN_BLOCKS, int TABLE, bool NORM>
+// CT: the constant-time mode of scalar_mul_core (JJ_CONST_TIME): table scan, selects, every addition executed.
+template <int THREADS, int MIN_BLOCKS, int TABLE, bool NORM, bool CT = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulArgs a) {
 #if defined(JJ_EXPERIMENTS)
     extern __shared__ uint4 smem_tbl[];
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_scalar_mul(const SmulAr
         {
             size_t gwarp = (size_t)blockIdx.x * (THREADS / 32) + warp;
             GmemTable t{a.tbl_scratch + gwarp * 32768 + lane * 32};
-            scalar_mul_core(acc, P, k.w, t);
+            scalar_mul_core<GmemTable, CT>(acc, P, k.w, t);
         }
         if (NORM) {
             fe run;

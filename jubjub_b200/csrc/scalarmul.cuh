@@ -63,8 +63,33 @@ struct LocalTable {
 #endif
 constexpr int kDoubleUnroll = JJ_DBL_UNROLL;  // unroll factor of the 4-doubling loop (code size vs register moves)
 
-// acc = [k] P.  `tbl` provides storage for the 8-entry window table.
+// Branch-free, address-uniform lookup for the constant-time mode: every entry is read (all lanes read the same address, so
+// the accesses are fully coalesced) and the wanted one is kept by selects; digit 0 yields the Niels identity (1, 1, 1, 0),
+// whose addition leaves the point unchanged (src/lib.rs:347-354), so the addition is always executed.
 template <class Table>
+JJ_DEVICE void table_scan(ext_niels& n, const Table& tbl, int mag) {  // mag = |digit| in [0, 8]
+    fe_set_one<FqP>(n.vpu);
+    fe_set_one<FqP>(n.vmu);
+    fe_set_one<FqP>(n.z);
+    fe_set_zero(n.t2d);
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+        ext_niels e;
+        tbl.load(j, e);
+        const bool hit = mag == j + 1;
+        fe_select(n.vpu, n.vpu, e.vpu, hit);
+        fe_select(n.vmu, n.vmu, e.vmu, hit);
+        fe_select(n.z, n.z, e.z, hit);
+        fe_select(n.t2d, n.t2d, e.t2d, hit);
+    }
+}
+
+// acc = [k] P.  `tbl` provides storage for the 8-entry window table.
+// CT = false (the *_vartime entry points): a zero digit skips its addition and the table is indexed by the digit.
+// CT = true (JJ_CONST_TIME): no branch and no address depends on the scalar -- the table is scanned, the sign is applied by
+// selects and the addition always runs -- the batch analogue of the reference's constant-time ladder, which always adds
+// "P or identity" (src/lib.rs:356-379).  Same values either way.
+template <class Table, bool CT = false>
 JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_t k[8], Table& tbl) {
     {
         ext_niels n1, nj;
@@ -98,7 +123,11 @@ JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_
         for (int j = 0; j < 4; j++) point_double(acc, acc);
         int d = (int)(K[7] >> 28) - 8;
         shl_256(K, 4);
-        if (d != 0) {
+        if (CT) {
+            ext_niels n;
+            table_scan(n, tbl, d < 0 ? -d : d);
+            point_add_niels(acc, acc, n, d < 0);  // operand and output halves chosen by selects
+        } else if (d != 0) {
             ext_niels n;
             tbl.load_signed((d < 0 ? -d : d) - 1, d < 0, n);
             point_add_niels_preswapped(acc, acc, n, d < 0);

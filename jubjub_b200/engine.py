@@ -206,9 +206,17 @@ class Engine:
         return {"extended": (EXT_W, np.uint64, 0), "affine": (AFF_W, np.uint64, L.JJ_OUT_AFFINE),
                 "bytes": (32, np.uint8, L.JJ_OUT_BYTES)}[output]
 
-    # The scalar-multiplication entry points are variable-time in the scalar (zero window digits skip their addition,
+    # The fast scalar-multiplication entry points are variable-time in the scalar (zero window digits skip their addition,
     # the table is indexed by the digit): the reference's `&ExtendedPoint * &Fr` is constant-time by policy
     # (src/lib.rs:12-17) and names every variable-time routine `*_vartime` (:14-15) -- so do these.  Public scalars only.
+    # `scalar_mul` (no suffix) is the constant-time-in-the-scalar mode of the same kernel (JJ_CONST_TIME).
+    def scalar_mul(self, points, scalars, output="extended", scalar_mont=False, out=None, flags=0):
+        """out[i] = [scalars[i]] points[i] with no branch or memory address depending on the scalars (window table
+        scanned, sign by selects, every addition executed -- the batch analogue of the reference's constant-time
+        `&ExtendedPoint * &Fr`, src/lib.rs:356-379, 873-879).  Same results as scalar_mul_vartime, slower."""
+        return self.scalar_mul_vartime(points, scalars, output=output, scalar_mont=scalar_mont, out=out,
+                                       flags=flags | L.JJ_CONST_TIME)
+
     def scalar_mul_vartime(self, points, scalars, output="extended", scalar_mont=False, out=None, flags=0):
         """out[i] = [scalars[i]] points[i]  (`&ExtendedPoint * &Fr`, src/lib.rs:873-879); variable-time."""
         w, dt, f = self._out_fmt(output)

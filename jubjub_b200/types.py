@@ -12,10 +12,11 @@ return `(value, is_some)` like `CtOption` (src/fr.rs:268-292, 438-540), a length
 scalar multiplication takes `Fr` in Montgomery form and ignores nothing but what `Fr` cannot hold.
 There is no CPU arithmetic here: without a B200 the engine constructor raises.
 
-Constant time: the reference's `*` is constant-time by policy (src/lib.rs:12-17); the batch engine's scalar
-multiplication is NOT (zero window digits skip their addition).  The explicit methods are therefore named
-`mul_vartime` / `batch_mul_vartime`, following the reference's naming rule (src/lib.rs:14-15), and the `*` operator
-on points refuses to run until the caller has acknowledged this once with `acknowledge_vartime()`.
+Constant time: the reference's `*` is constant-time by policy (src/lib.rs:12-17).  Here `point * scalar` runs the
+engine's constant-time-in-the-scalar kernel mode (JJ_CONST_TIME: no branch or address depends on the scalar); the
+fast variable-time kernels are reached through explicitly named methods, `mul_vartime` / `batch_mul_vartime`, following
+the reference's naming rule (src/lib.rs:14-15) -- or through `*` after the caller has opted in once with
+`acknowledge_vartime()` (public scalars only).
 """
 import numpy as np
 
@@ -28,16 +29,11 @@ _EDWARDS_D2_RAW = 0x552631CE97F45691EBFB240FCD7AFFA8525AFEDA6EAF3A4C020CBFADAC68
 _VARTIME_ACK = False
 
 
-def acknowledge_vartime():
-    """Opt in to `point * scalar` operators: they run the variable-time batch kernels (public scalars only)."""
+def acknowledge_vartime(on=True):
+    """Let the `point * scalar` operators run the fast variable-time kernels (public scalars only).  Without it they run
+    the constant-time mode."""
     global _VARTIME_ACK
-    _VARTIME_ACK = True
-
-
-def _need_ack():
-    if not _VARTIME_ACK:
-        raise RuntimeError("point * scalar runs a variable-time kernel (the reference's `*` is constant-time, "
-                           "src/lib.rs:12-17): use mul_vartime(), or call jubjub_b200.types.acknowledge_vartime() once")
+    _VARTIME_ACK = bool(on)
 
 
 def _limbs(x):
@@ -292,10 +288,10 @@ class AffinePoint:
         return self.to_extended().mul_vartime(k)
 
     def __mul__(self, k):
+        """`&AffinePoint * &Fr`: constant-time in the scalar unless acknowledge_vartime() was called."""
         if not isinstance(k, Fr):
             return NotImplemented
-        _need_ack()
-        return self.mul_vartime(k)
+        return self.mul_vartime(k) if _VARTIME_ACK else self.to_extended() * k
 
     def mul_by_cofactor(self):
         return self.to_extended().mul_by_cofactor()
@@ -372,10 +368,14 @@ class ExtendedPoint:
         return ExtendedPoint(self.eng.scalar_mul_vartime(self.data, k.limbs, scalar_mont=True), self.eng)
 
     def __mul__(self, k):
+        """`&ExtendedPoint * &Fr` (src/lib.rs:873-879): constant-time in the scalar (JJ_CONST_TIME) unless
+        acknowledge_vartime() was called."""
         if not isinstance(k, Fr):
             return NotImplemented
-        _need_ack()
-        return self.mul_vartime(k)
+        if _VARTIME_ACK:
+            return self.mul_vartime(k)
+        self._same(k)
+        return ExtendedPoint(self.eng.scalar_mul(self.data, k.limbs, scalar_mont=True), self.eng)
 
     def multiply_bits(self, by):
         """[k]P for 32 little-endian bytes per point, top four bits ignored (src/lib.rs:381-385)."""

@@ -85,6 +85,7 @@ def main():
         eng.set_scalar_mul_variant(v)
         rec(f"scalar_mul -> bytes ({name})", timed(eng, lambda: eng._check(eng.lib.jj_scalar_mul(
             eng.ctx, p.ptr, k.ptr, outb.ptr, n, jj.JJ_DEVICE_PTRS | A | jj.JJ_OUT_BYTES)), reps=3, warm=1), 224)
+    rec("scalar_mul (JJ_CONST_TIME)", timed(eng, lambda: eng.scalar_mul(p, k, out=o, flags=A), reps=3), 352)
     eng.set_scalar_mul_variant(24)
     rec("scalar_mul (24 warps/SM)", timed(eng, lambda: eng.scalar_mul_vartime(p, k, out=o, flags=A), reps=3), 352)
     eng.set_scalar_mul_variant(0)

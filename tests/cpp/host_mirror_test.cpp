@@ -30,6 +30,10 @@ int main(int argc, char** argv) {
                 std::printf("mismatch at %llu\n", (unsigned long long)i);
                 return 1;
             }
+        // constant-time mode: the same points
+        auto enc_ct = eng.batch_to_bytes(eng.batch_normalize(eng.batch_mul(p, k)));
+        for (uint64_t i = 0; i < n; i++)
+            if (std::memcmp(enc_ct[i].data(), want[i].data(), 32) != 0) return 12;
         // p + p == p.double() (projectively): compare through normalisation
         auto a = eng.batch_normalize(eng.batch_add(p, p));
         auto d = eng.batch_normalize(eng.batch_double(p));

@@ -74,6 +74,15 @@ extern "C" void emul_scalar_mul(const void* p_, const void* k_, void* out_, size
         ((ext_point*)out_)[i] = acc;
     }
 }
+// the constant-time mode of the same core (table scan, selects, every addition executed)
+extern "C" void emul_scalar_mul_ct(const void* p_, const void* k_, void* out_, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        LocalTable tbl;
+        ext_point acc;
+        scalar_mul_core<LocalTable, true>(acc, ((const ext_point*)p_)[i], ((const uint32_t*)k_) + 8 * i, tbl);
+        ((ext_point*)out_)[i] = acc;
+    }
+}
 // one scalar k (32 LE bytes) for all points: the width-5 NAF path of is_torsion_free
 extern "C" int emul_scalar_mul_wnaf(const void* p_, const void* k_, void* out_, size_t n) {
     NafDigits naf;

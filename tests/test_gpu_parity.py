@@ -269,6 +269,25 @@ def test_scalar_mul_variants(eng, oracle, variant):
         eng.set_scalar_mul_variant(0)
 
 
+def test_scalar_mul_constant_time_mode(eng, oracle):
+    """JJ_CONST_TIME (Engine.scalar_mul, and `point * scalar` of the reference-style types): same results as the oracle's
+    constant-time ladder for every edge scalar, in every output format, host and device resident."""
+    p, k = _smul_case(oracle, 3000)
+    want_ext = oracle.scalar_mul(p, k)
+    want_aff = oracle.batch_normalize(want_ext)
+    got = eng.scalar_mul(p, k)
+    assert oracle.ext_eq(got, want_ext).all() and (oracle.batch_normalize(got) == want_aff).all()
+    assert (eng.scalar_mul(p, k, output="affine") == want_aff).all()
+    assert (eng.scalar_mul(p, k, output="bytes") == oracle.affine_to_bytes(want_aff)).all()
+    assert (eng.scalar_mul(eng.to_device(p), eng.to_device(k), output="bytes").download() == oracle.affine_to_bytes(want_aff)).all()
+    s = oracle.fe_stream(FR, 123, len(p))
+    assert (eng.scalar_mul(p, s, scalar_mont=True, output="affine")
+            == oracle.batch_normalize(oracle.scalar_mul(p, oracle.fe_to_bytes(FR, s)))).all()
+    # all-zero scalars: 63 identity additions
+    z = np.zeros((64, 32), np.uint8)
+    assert oracle.is_identity(eng.scalar_mul(p[:64], z)).all()
+
+
 def test_scalar_mul_vs_bigint_model(eng, oracle):
     p, k = _smul_case(oracle, 40)
     vals = oracle.fe_to_bytes(FQ, oracle.batch_normalize(p).reshape(-1, 4)).reshape(-1, 64)

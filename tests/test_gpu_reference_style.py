@@ -12,15 +12,19 @@ pytestmark = pytest.mark.gpu
 def T():
     from jubjub_b200 import types
 
-    # `point * scalar` runs a variable-time kernel (the reference's `*` is constant-time, src/lib.rs:12-17): the
-    # operator refuses until the caller opts in; mul_vartime() is the explicitly named form
+    # `point * scalar` is constant-time in the scalar like the reference's (src/lib.rs:12-17): it runs the JJ_CONST_TIME
+    # kernel mode; mul_vartime() is the explicitly named fast form.  These tests run the operators in BOTH modes.
+    types.acknowledge_vartime(False)
     p = types.ExtendedPoint.identity()
-    if not types._VARTIME_ACK:
-        with pytest.raises(RuntimeError):
-            p * types.Fr.one()
-    assert p.mul_vartime(types.Fr.one()).is_identity()[0]
-    types.acknowledge_vartime()
+    assert (p * types.Fr.one()).is_identity()[0] and p.mul_vartime(types.Fr.one()).is_identity()[0]
     return types
+
+
+@pytest.fixture(params=["constant-time", "vartime"], autouse=True)
+def _operator_mode(request, T):
+    T.acknowledge_vartime(request.param == "vartime")
+    yield
+    T.acknowledge_vartime(False)
 
 
 def _raw(limbs):

@@ -106,6 +106,13 @@ def emul(built):
             return out
 
         @staticmethod
+        def smul_ct(p, k):
+            out = np.empty_like(p)
+            lib.emul_scalar_mul_ct(p.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),
+                                   out.ctypes.data_as(C.c_void_p), C.c_size_t(len(p)))
+            return out
+
+        @staticmethod
         def fixed_entries(base, w, first, count):
             tbl = np.zeros(lib.emul_fixed_table_words(w), dtype=np.uint32)
             lib.emul_fixed_table(base.ctypes.data_as(C.c_void_p), tbl.ctypes.data_as(C.c_void_p), w, first, count)
@@ -209,6 +216,11 @@ def test_emulated_points_and_scalar_mul(emul, oracle):
     got = emul.smul(pp, k)
     assert oracle.ext_eq(got, want).all()
     assert (oracle.batch_normalize(got) == oracle.batch_normalize(want)).all()
+    # constant-time mode (table scan, selects, every addition executed, identity for digit 0): the same points; the
+    # projective representation may differ from the variable-time core's only where a zero digit added the identity
+    got_ct = emul.smul_ct(pp, k)
+    assert oracle.ext_eq(got_ct, want).all()
+    assert (oracle.batch_normalize(got_ct) == oracle.batch_normalize(want)).all()
     want = oracle.batch_normalize(oracle.scalar_mul_fixed(oracle.generator(), k))
     for w in (4, 7):  # both window widths of the fixed-base table
         # the table the device kernel builds, computed here by the oracle: entry e = (j+1) * 2^(w*i) * G
@@ -366,4 +378,54 @@ def test_types_star_import_and_vartime_gate():
 
     for name in ("scalar_mul_vartime", "scalar_mul_fixed_vartime", "scalar_mul_encoded_vartime", "scalar_mul_sharded_vartime"):
         assert hasattr(jj.Engine, name), name
-    assert not hasattr(jj.Engine, "scalar_mul")
+    # the unsuffixed name is the constant-time-in-the-scalar mode, like the reference's `*`
+    assert "JJ_CONST_TIME" in jj.Engine.scalar_mul.__code__.co_names or "constant" in (jj.Engine.scalar_mul.__doc__ or "")
+    for name in ("scalar_mul_fixed", "scalar_mul_encoded", "scalar_mul_sharded"):
+        assert not hasattr(jj.Engine, name), name  # no constant-time mode there: only the *_vartime names exist
+
+
+def test_constant_time_kernel_has_no_scalar_dependent_branch(built):
+    """Structural check of JJ_CONST_TIME on the shipped SASS: inside the window loop of the constant-time kernel the only
+    control flow is the three loop back-edges (4 doublings, 8-entry table scan, 63 windows) and the calls of the shared
+    Fq product -- no BSSY / BSYNC reconvergence pair, i.e. no divergent branch on the digit -- and the table loads sit in
+    the scan loop (4 per iteration), not behind a digit-indexed address.  The variable-time kernel, for contrast, has the
+    divergent `if (digit != 0)`."""
+    import subprocess
+
+    from jubjub_b200 import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = funcs.setdefault(m.group(1), [])
+            continue
+        m = re.match(r"^\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m and cur is not None:
+            cur.append((int(m.group(1), 16), m.group(2).strip()))
+
+    def window_loop(name_part):
+        (ins,) = [v for k, v in funcs.items() if name_part in k]
+        back = []
+        for a, t in ins:
+            m = re.match(r"(?:@!?U?P\d+\s+)?BRA\s+0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) < a:
+                back.append((int(m.group(1), 16), a))
+        # the window loop: the innermost loop that contains the 8 calls of one addition
+        loops = sorted(back, key=lambda r: r[1] - r[0])
+        for lo, hi in loops:
+            body = [(a, t) for a, t in ins if lo <= a <= hi]
+            if sum("CALL" in t for _, t in body) == 8:
+                return body, [(l, h) for l, h in back if lo <= l and h <= hi]
+        raise AssertionError("window loop not found")
+
+    ct, ct_back = window_loop("k_scalar_mulILi512ELi1ELi1ELb0ELb1")
+    vt, _ = window_loop("k_scalar_mulILi512ELi1ELi1ELb0ELb0")
+    assert not any(re.search(r"\b(BSSY|BSYNC|WARPSYNC)\b", t) for _, t in ct)
+    bras = [t for _, t in ct if re.search(r"\bBRA\b", t)]
+    assert len(bras) == 3 and len(ct_back) == 3, bras          # doubling loop, scan loop, window loop: back-edges only
+    scan = min((r for r in ct_back), key=lambda r: r[1] - r[0])
+    loads = [(a, t) for a, t in ct if "LDG" in t]
+    assert len(loads) == 4 and all(scan[0] <= a <= scan[1] for a, _ in loads)
+    assert any(re.search(r"\bBSSY\b", t) for _, t in vt)        # the variable-time kernel does branch on the digit
