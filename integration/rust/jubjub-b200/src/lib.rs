@@ -203,6 +203,24 @@ impl Engine {
     /// (`AffinePoint::from_bytes`, `src/lib.rs:470-483`), multiplied by `scalars[i]`, and encoded again.
     /// `ok[i] == 0` marks an encoding the reference would reject (`CtOption::none`); its output is unspecified.
     pub fn batch_mul_encoded_vartime(&self, encodings: &[[u8; 32]], scalars: &[Fr]) -> Result<(Vec<[u8; 32]>, Vec<u8>), Error> {
+        self.batch_mul_encoded_flags(encodings, scalars, 0)
+    }
+
+    /// The same with the kernel's constant-time-in-the-scalar mode (`JJ_CONST_TIME`): no branch and no memory address
+    /// depends on `scalars` (window table scanned, sign by selects, every addition executed -- the batch analogue of the
+    /// reference's "always add P or identity", `src/lib.rs:356-379`).  About 4 % slower; the points stay public data.
+    /// This is the entry point that keeps the reference's policy (`src/lib.rs:12-17`), hence no `_vartime` suffix.
+    pub fn batch_mul_encoded(&self, encodings: &[[u8; 32]], scalars: &[Fr]) -> Result<(Vec<[u8; 32]>, Vec<u8>), Error> {
+        self.batch_mul_encoded_flags(encodings, scalars, JJ_CONST_TIME)
+    }
+
+    /// `SubgroupPoint::from_bytes(..)` semantics for the decode (`src/lib.rs:1427-1429`): `ok[i]` also requires the point to
+    /// be torsion free (decided on the device by a pairing, not by `[r]P`), then the multiplication.
+    pub fn batch_mul_encoded_subgroup_vartime(&self, encodings: &[[u8; 32]], scalars: &[Fr]) -> Result<(Vec<[u8; 32]>, Vec<u8>), Error> {
+        self.batch_mul_encoded_flags(encodings, scalars, JJ_CHECK_SUBGROUP)
+    }
+
+    fn batch_mul_encoded_flags(&self, encodings: &[[u8; 32]], scalars: &[Fr], flags: u32) -> Result<(Vec<[u8; 32]>, Vec<u8>), Error> {
         assert_eq!(encodings.len(), scalars.len());
         let n = encodings.len();
         let k: Vec<[u8; 32]> = scalars.iter().map(|s| s.to_bytes()).collect(); // src/fr.rs:296-308
@@ -216,7 +234,7 @@ impl Engine {
                 out.as_mut_ptr() as *mut c_void,
                 ok.as_mut_ptr(),
                 n,
-                JJ_OUT_BYTES,
+                JJ_OUT_BYTES | flags,
             )
         };
         self.check(rc)?;
