@@ -2,6 +2,7 @@
 # Multi-GPU pass: at N=2 the 2-GPU parity test (log kept), then bench.py at N ranks (fused P2P gather and, unless
 # SKIP_NCCL, ncclAllGather).  Everything lands in gpurun_out/<tag>_*.
 N=${1:-2}; tag=${2:-run}
+python -c "import __graft_entry__ as g; g.build()" || exit 1
 mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
   timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu -rs > gpurun_out/${tag}_pytest_gpu_multi_n2.txt 2>&1

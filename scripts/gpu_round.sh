@@ -2,6 +2,7 @@
 # One GPU-box pass for a milestone: parity tests, bench lines, per-kernel throughput, ncu launch list and
 # a full ncu capture of the dominant kernel.  Everything lands in gpurun_out/<tag>_*.
 tag=${1:-run}
+python -c "import __graft_entry__ as g; g.build()" || exit 1  # content-hash check: rebuilds only if the sources changed
 mkdir -p gpurun_out
 if [ -z "$SKIP_TESTS" ]; then
 timeout 1500 python -m pytest tests -x -q -m gpu -rs --durations=15 > gpurun_out/${tag}_pytest_gpu.txt 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest_gpu.txt

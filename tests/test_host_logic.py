@@ -361,6 +361,10 @@ def test_build_records_the_validated_nvcc(built):
 
     info = json.load(open(os.path.join(ROOT, "jubjub_b200", "build_info.json")))
     assert info["nvcc"] == built.VALIDATED_NVCC, info
+    # the library on disk was built from exactly the sources on disk (content hash, not file times)
+    csrc = os.path.join(ROOT, "jubjub_b200", "csrc")
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))] + [os.path.join(ROOT, "include", "jubjub_b200.h")]
+    assert info["sources_sha256"] == built._sources_digest(srcs, " ".join(info["flags"]))
     assert "-lineinfo" in info["flags"] and "arch=compute_100a,code=sm_100a" in info["flags"]
 
 
