@@ -611,6 +611,28 @@ def test_error_behaviour(eng, oracle):
     assert b"aligned" in eng.lib.jj_last_error(eng.ctx)
     assert eng.lib.jj_set_scalar_mul_variant(eng.ctx, 99) == -1
     assert eng.lib.jj_set_scalar_mul_variant(eng.ctx, 15) == -1  # experimental mappings are not in the default build
+    # new entry points validate their arguments the same way
+    p, k = _smul_case(oracle, 40)
+    enc = oracle.affine_to_bytes(oracle.batch_normalize(p))
+    out = np.zeros((len(p), 32), np.uint8)
+    rc = eng.lib.jj_scalar_mul_encoded(eng.ctx, enc.ctypes.data, k.ctypes.data, out.ctypes.data, None, len(p),
+                                       jj.JJ_OUT_BYTES | jj.JJ_CHECK_SUBGROUP)
+    assert rc == -1 and b"ok[]" in eng.lib.jj_last_error(eng.ctx)        # the subgroup flag needs somewhere to go
+    rc = eng.lib.jj_scalar_mul_encoded(eng.ctx, enc.ctypes.data, k.ctypes.data, out.ctypes.data, None, len(p), jj.JJ_OUT_BYTES)
+    assert rc == 0 and (out == oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(p, k)))).all()  # ok[] is optional
+    eng.set_scalar_mul_variant(24)
+    try:
+        with pytest.raises(jj.JubjubError):  # the constant-time mode exists for the default mapping only
+            eng.scalar_mul(p, k)
+    finally:
+        eng.set_scalar_mul_variant(0)
+    assert eng.lib.jj_mul_by_cofactor(eng.ctx, None, out.ctypes.data, 4, 0) == -1
+    assert eng.lib.jj_is_prime_order(eng.ctx, p.ctypes.data, None, 4, 0) == -1
+    assert eng.lib.jj_scalar_mul_sharded_n(eng.ctx, p.ctypes.data, k.ctypes.data, None, None, 4, 0) == -1
+    # single rank: the sharded entry points degenerate to the plain call (no communicator needed)
+    d_out = eng.empty((len(p), 20))
+    eng.scalar_mul_sharded_vartime(p, k, d_out, n_total=len(p))
+    assert (eng.batch_normalize(d_out.download()) == oracle.batch_normalize(oracle.scalar_mul(p, k))).all()
     ctx = C.c_void_p()
     assert eng.lib.jj_init(10_000, C.byref(ctx)) == -1
 
