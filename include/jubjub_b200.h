@@ -192,6 +192,12 @@ int32_t jj_scalar_mul_encoded(jj_ctx* ctx, const void* points32, const void* sca
 /* out[i] = [scalars[i]] base: `&AffinePoint * &Fr` src/lib.rs:1109-1115 -> AffineNielsPoint::multiply :271-295,
  * one shared base; the per-window AffineNiels table is built once per base and cached in ctx. */
 int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* scalars32, void* out, size_t n, uint32_t flags);
+/* Sum<ExtendedPoint> src/lib.rs:183-193 (`iter.fold(identity, |acc, p| acc + p)`; SubgroupPoint :1161-1171), batched: the
+ * input holds `groups` consecutive groups of `group_size` points, out[j] = sum of group j (groups = 1: one sum of the
+ * whole batch; group_size = 0: identities).  Together with jj_scalar_mul this is sum_i [k_i] P_i on the device.  The
+ * association order is a tree, not the reference's left fold: the result is the same point in other projective
+ * coordinates -- JJ_OUT_AFFINE / JJ_OUT_BYTES outputs are bit-exact.  Host or device pointers; not capturable. */
+int32_t jj_point_sum(jj_ctx* ctx, const void* points_ext, void* out, size_t groups, size_t group_size, uint32_t flags);
 /* ExtendedPoint::mul_by_cofactor src/lib.rs:722-724 (= double().double().double(), all 160 B bit-exact) */
 int32_t jj_mul_by_cofactor(jj_ctx* ctx, const void* p_ext, void* out_ext, size_t n, uint32_t flags);
 /* ExtendedPoint::batch_normalize src/lib.rs:840-858: ExtendedPoint -> AffinePoint (z = 0 gives (0, 0)

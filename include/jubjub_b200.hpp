@@ -101,6 +101,15 @@ class Engine {
         check(jj_point_add_niels(ctx_, p.data(), q.data(), out.data(), p.size(), subtract ? JJ_SUBTRACT : 0));
         return out;
     }
+    // Sum<ExtendedPoint> (src/lib.rs:183-193) of consecutive groups of `group_size` points (0 = the whole batch)
+    std::vector<ExtendedPoint> batch_sum(const std::vector<ExtendedPoint>& p, size_t group_size = 0) {
+        const size_t g = group_size ? group_size : p.size();
+        if (g && p.size() % g) throw Error(JJ_ERR_INVALID_ARG, "batch does not split into groups of that size");
+        const size_t groups = g ? p.size() / g : 1;
+        std::vector<ExtendedPoint> out(groups);
+        check(jj_point_sum(ctx_, p.data(), out.data(), groups, g, 0));
+        return out;
+    }
     std::vector<ExtendedPoint> batch_double(const std::vector<ExtendedPoint>& p) {
         std::vector<ExtendedPoint> out(p.size());
         check(jj_point_double(ctx_, p.data(), out.data(), p.size(), 0));

@@ -118,6 +118,7 @@ extern "C" {
     pub fn jj_scalar_mul(ctx: *mut JjCtx, points_ext: *const c_void, scalars32: *const c_void, out: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_scalar_mul_encoded(ctx: *mut JjCtx, points32: *const c_void, scalars32: *const c_void, out: *mut c_void, ok: *mut u8, n: usize, flags: u32) -> i32;
     pub fn jj_scalar_mul_fixed(ctx: *mut JjCtx, base_affine: *const c_void, scalars32: *const c_void, out: *mut c_void, n: usize, flags: u32) -> i32;
+    pub fn jj_point_sum(ctx: *mut JjCtx, points_ext: *const c_void, out: *mut c_void, groups: usize, group_size: usize, flags: u32) -> i32;
     pub fn jj_mul_by_cofactor(ctx: *mut JjCtx, p_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_batch_normalize(ctx: *mut JjCtx, in_ext: *const c_void, out_affine: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_batch_normalize_extended(ctx: *mut JjCtx, in_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -992,6 +993,72 @@ int32_t jj_mul_by_cofactor(jj_ctx* c, const void* p, void* out, size_t n, uint32
         CU(c, cudaGetLastError());
         return JJ_OK;
     });
+}
+
+int32_t jj_point_sum(jj_ctx* c, const void* points, void* out, size_t groups, size_t group_size, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    if (groups && (!points || !out)) return fail(c, JJ_ERR_INVALID_ARG, "null pointer");
+    CU(c, cudaSetDevice(c->device));
+    if (capturing(c)) return fail(c, JJ_ERR_INVALID_ARG, "jj_point_sum cannot be captured into a graph");
+    if (groups == 0) return JJ_OK;
+    const bool dev = flags & JJ_DEVICE_PTRS;
+    const size_t unit = out_unit(flags);
+    cudaStream_t s = c->stream;
+    if (group_size == 0) {  // empty sums are the identity (the fold's initial value)
+        std::vector<uint64_t> id(groups * 20, 0);
+        const uint64_t one[4] = {0x00000001fffffffeull, 0x5884b7fa00034802ull, 0x998c4fefecbc4ff5ull, 0x1824b159acc5056full};
+        for (size_t gidx = 0; gidx < groups; gidx++)
+            for (int w = 0; w < 4; w++) id[gidx * 20 + 4 + w] = id[gidx * 20 + 8 + w] = one[w];
+        if (unit != 160) return fail(c, JJ_ERR_INVALID_ARG, "empty groups are supported for ExtendedPoint output only");
+        if (dev) CU(c, cudaMemcpy(out, id.data(), groups * 160, cudaMemcpyHostToDevice));
+        else memcpy(out, id.data(), groups * 160);
+        return JJ_OK;
+    }
+    constexpr int F = 16;
+    const size_t n = groups * group_size;
+    // device-resident input (uploaded in one piece for host callers: 160 B per point, the kernels are HBM-bound)
+    const char* cur = (const char*)points;
+    if (!dev) {
+        int32_t rc = ensure(c, &c->tmp, &c->tmp_cap, n * 160);
+        if (rc) return rc;
+        CU(c, cudaMemcpyAsync(c->tmp, points, n * 160, cudaMemcpyHostToDevice, s));
+        cur = c->tmp;
+    } else if ((uintptr_t)points & 31 || (uintptr_t)out & 31) {
+        return fail(c, JJ_ERR_INVALID_ARG, "device pointer not 32-byte aligned");
+    }
+    // ping-pong partial sums in the normalise scratch
+    const size_t per1 = (group_size + F - 1) / F;
+    int32_t rc = ensure(c, &c->norm, &c->norm_cap, 2 * groups * per1 * 160 + 64);
+    if (rc) return rc;
+    char* buf[2] = {c->norm, c->norm + ((groups * per1 * 160 + 31) & ~(size_t)31)};
+    size_t g = group_size;
+    int which = 0;
+    while (g > 1) {
+        const size_t per = (g + F - 1) / F;
+        k_point_sum_pass<F><<<grid_for(c, groups * per, 128, 4), 128, 0, s>>>(cur, buf[which], groups, g);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        cur = buf[which];
+        which ^= 1;
+        g = per;
+    }
+    // cur: one ExtendedPoint per group -> requested output format
+    char* dst = dev ? (char*)out : nullptr;
+    if (!dev) {
+        rc = ensure(c, &c->tmp2, &c->tmp2_cap, groups * 160 + groups * 32);
+        if (rc) return rc;
+        dst = c->tmp2;
+    }
+    if (unit == 160) {
+        CU(c, cudaMemcpyAsync(dst, cur, groups * 160, cudaMemcpyDeviceToDevice, s));
+    } else {
+        rc = normalize_launch(c, s, cur, dst, groups, (int)unit, &c->tbl, &c->tbl_cap, true);
+        if (rc) return rc;
+    }
+    if (!dev) CU(c, cudaMemcpyAsync(out, dst, groups * unit, cudaMemcpyDeviceToHost, s));
+    if (!dev || !(flags & JJ_ASYNC)) CU(c, cudaStreamSynchronize(s));
+    return JJ_OK;
 }
 
 int32_t jj_scalar_mul(jj_ctx* c, const void* points, const void* scalars, void* out, size_t n, uint32_t flags) {

@@ -299,6 +299,30 @@ __global__ void __launch_bounds__(128) k_mul_by_cofactor(const char* __restrict_
         st_ext(out, i, P);
     }
 }
+// Sum<ExtendedPoint> (src/lib.rs:183-193: `iter.fold(identity, |acc, item| acc + item)`), batched and grouped: the input is
+// `groups` consecutive groups of `g` points; one pass replaces every group by ceil(g / F) partial sums (thread t of a group
+// adds the F consecutive points [tF, tF + F) of that group with the reference's `&ExtendedPoint + &ExtendedPoint`,
+// :992-999), and the host repeats the pass until one point per group is left.  The association order differs from the
+// reference's left fold, so the projective coordinates do; the point (normalised / encoded) is the same.
+template <int F>
+__global__ void __launch_bounds__(128) k_point_sum_pass(const char* __restrict__ in, char* __restrict__ out, size_t groups,
+                                                        size_t g) {
+    const size_t per = (g + F - 1) / F;  // partial sums per group after this pass
+    const size_t total = groups * per, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        const size_t grp = w / per, t = w % per;
+        const size_t lo = t * F, hi = lo + F < g ? lo + F : g;
+        ext_point acc, q;
+        ld_ext(acc, in, grp * g + lo);
+#pragma unroll 1
+        for (size_t i = lo + 1; i < hi; i++) {
+            ld_ext(q, in, grp * g + i);
+            point_add(acc, acc, q, false);
+        }
+        st_ext(out, w, acc);
+    }
+}
+
 // Subgroup membership by the order-8 Tate pairing (torsion.cuh) -- is_torsion_free (src/lib.rs:709-711) and,
 // with PRIME_ORDER, is_prime_order (:717-719: torsion free and not the identity).  STRIDE is the byte size of one
 // input point: 160 (ExtendedPoint) or 64 (AffinePoint, z = 1).  With AND_INTO the result is combined with the flag

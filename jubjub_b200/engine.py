@@ -261,6 +261,21 @@ class Engine:
         overwrites `p` like the reference's `&mut [ExtendedPoint]`."""
         return self._call("jj_batch_normalize_extended", [(p, EXT_W, np.uint64)], EXT_W, out=p if in_place else None)
 
+    def point_sum(self, p, group_size=None, output="extended"):
+        """Sum<ExtendedPoint> (src/lib.rs:183-193) over consecutive groups of `group_size` points (default: the whole
+        batch -> one point).  Returns one point per group in the requested format."""
+        w, dt, f = self._out_fmt(output)
+        ptr, n, dev, keep = self._arg(p, EXT_W, np.uint64)
+        g = n if group_size is None else int(group_size)
+        if g < 0 or (g and n % g):
+            raise JubjubError(-1, f"{n} points do not split into groups of {g}")
+        groups = (n // g) if g else 1
+        if n == 0:
+            groups, g = 1, 0
+        o = self._out(dev, groups, w, dt)
+        self._check(self.lib.jj_point_sum(self.ctx, ptr, self._ptr(o), groups, g, f | (L.JJ_DEVICE_PTRS if dev else 0)))
+        return o
+
     def mul_by_cofactor(self, p, out=None):
         """ExtendedPoint::mul_by_cofactor (src/lib.rs:722-724)."""
         return self._call("jj_mul_by_cofactor", [(p, EXT_W, np.uint64)], EXT_W, out=out)

@@ -385,6 +385,10 @@ class ExtendedPoint:
         """src/lib.rs:722-724."""
         return ExtendedPoint(self.eng.mul_by_cofactor(self.data), self.eng)
 
+    def sum(self):
+        """Sum<ExtendedPoint> (src/lib.rs:183-193): the sum of the whole batch, a batch of one point."""
+        return ExtendedPoint(self.eng.point_sum(self.data), self.eng)
+
     def is_identity(self):
         return self.eng.is_identity(self.data)
 

@@ -60,6 +60,12 @@ def main():
     nq = eng.point_to_niels(q)
     rec("point_add_niels", timed(eng, lambda: eng._check(eng.lib.jj_point_add_niels(eng.ctx, p.ptr, nq.ptr, o.ptr, n, jj.JJ_DEVICE_PTRS | A))), 448)
     rec("scalar_mul (variable base)", timed(eng, lambda: eng.scalar_mul_vartime(p, k, out=o, flags=A), reps=3), 352)
+    one = eng.empty((1, 20))
+    rec("point_sum (one sum of the batch)", timed(eng, lambda: eng._check(eng.lib.jj_point_sum(
+        eng.ctx, o.ptr, one.ptr, 1, n, jj.JJ_DEVICE_PTRS | A))), 160)
+    grp = eng.empty((n // 64, 20))
+    rec("point_sum (groups of 64)", timed(eng, lambda: eng._check(eng.lib.jj_point_sum(
+        eng.ctx, o.ptr, grp.ptr, n // 64, 64, jj.JJ_DEVICE_PTRS | A))), 162.5)
     aff = eng.empty((n, 8))
     rec("batch_normalize", timed(eng, lambda: eng.batch_normalize(o, out=aff)), 224)
     enc = eng.empty((n, 32), np.uint8)

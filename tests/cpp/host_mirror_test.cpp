@@ -56,6 +56,13 @@ int main(int argc, char** argv) {
         auto tf = eng.batch_is_torsion_free(c8), po = eng.batch_is_prime_order(c8);
         for (uint64_t i = 0; i < n; i++)
             if (!tf[i] || !po[i]) return 11;  // [8]P lies in the prime-order subgroup (and is not O for these inputs)
+        // Sum: p0 + p1 + ... in groups of n/2 and as one sum; (sum of halves) == whole sum
+        if (n >= 4 && n % 2 == 0) {
+            auto halves = eng.batch_sum(p, n / 2);
+            auto whole = eng.batch_normalize(eng.batch_sum(p));
+            auto again = eng.batch_normalize(eng.batch_sum(halves));
+            if (std::memcmp(whole.data(), again.data(), sizeof(AffinePoint)) != 0) return 13;
+        }
         bool threw = false;
         try {
             k.pop_back();

@@ -388,6 +388,55 @@ def test_batch_normalize_and_flags(eng, oracle):
     assert (eng.mul_by_cofactor(q) == oracle.ext_mul_by_cofactor(q)).all()
 
 
+def _oracle_sum(oracle, p):
+    """Sum of the rows of p by halving with the oracle's `&ExtendedPoint + &ExtendedPoint` (any order gives the same point)."""
+    p = p.copy()
+    while len(p) > 1:
+        if len(p) % 2:
+            p = np.concatenate([p, oracle.identity()])
+        h = len(p) // 2
+        p = oracle.ext_add(np.ascontiguousarray(p[:h]), np.ascontiguousarray(p[h:]))
+    return p
+
+
+def test_point_sum(eng, oracle):
+    """Sum<ExtendedPoint> (src/lib.rs:183-193) batched and grouped: whole-batch sums, group sums (sizes that are and are
+    not multiples of the per-thread chain), every output format, host and device; and with jj_scalar_mul in front of it the
+    multi-scalar product sum_i [k_i] P_i against the oracle."""
+    p = oracle.ext_double(_points(oracle, 5040 - 9))            # 5040 points incl. identity and the 8-torsion, z != 1
+    want = oracle.batch_normalize(_oracle_sum(oracle, p))
+    got = eng.point_sum(p)
+    assert got.shape == (1, 20) and (oracle.batch_normalize(got) == want).all()
+    assert (eng.point_sum(p, output="affine") == want).all()
+    assert (eng.point_sum(p, output="bytes") == oracle.affine_to_bytes(want)).all()
+    assert (eng.point_sum(eng.to_device(p), output="affine").download() == want).all()
+    for g in (1, 2, 5, 16, 40, 252, 1008):  # below, at and above the 16-point chain of one thread, with ragged tails
+        sums = eng.point_sum(p, group_size=g, output="affine")
+        assert sums.shape == (5040 // g, 8)
+        for j in (0, 1, 5040 // g - 1):
+            assert (sums[j] == oracle.batch_normalize(_oracle_sum(oracle, p[j * g:(j + 1) * g]))[0]).all(), (g, j)
+    assert oracle.is_identity(eng.point_sum(np.zeros((0, 20), np.uint64))).all()   # the empty sum is the identity
+    with pytest.raises(Exception):
+        eng.point_sum(p, group_size=11)                                             # 5040 is not a multiple of 11
+    # sum_i [k_i] P_i on the device: scalar-mul results stay in HBM, then one sum
+    n = 1 << 16
+    t = eng.fe_to_bytes("fr", eng.fe_stream("fr", 9001, n, device=True))
+    k = eng.fe_to_bytes("fr", eng.fe_stream("fr", 9002, n, device=True))
+    pts = eng.scalar_mul_fixed_vartime(oracle.generator(), t)
+    msm = eng.point_sum(eng.scalar_mul_vartime(pts, k), output="affine").download()
+    # [k_i][t_i]G summed = [sum k_i t_i mod 8r] G: checked through Fr arithmetic on the prime-order part instead of 65 536
+    # oracle scalar-muls: multiply everything by the cofactor so that the scalars live in Fr
+    kt = oracle.fe_batch(FR, oracle.OP_MUL, oracle.fe_stream(FR, 9001, n), oracle.fe_stream(FR, 9002, n))
+    acc = kt.copy()
+    while len(acc) > 1:
+        h = len(acc) // 2
+        acc = oracle.fe_batch(FR, oracle.OP_ADD, np.ascontiguousarray(acc[:h]), np.ascontiguousarray(acc[h:]))
+    g8 = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(oracle.generator()))
+    want8 = oracle.batch_normalize(oracle.scalar_mul(g8, oracle.fe_to_bytes(FR, acc)))
+    got8 = oracle.batch_normalize(oracle.ext_mul_by_cofactor(oracle.affine_to_extended(msm)))
+    assert (got8 == want8).all()
+
+
 def test_batch_normalize_extended_in_place(eng, oracle):
     """The free function batch_normalize (src/lib.rs:1084-1107): the ExtendedPoints themselves are normalised
     (z = 1, t1 = u, t2 = v), in place on the host and on the device; z = 0 ends as (0, 0, 1, 0, 0)."""
