@@ -242,6 +242,11 @@ int32_t jj_scalar_mul_sharded(jj_ctx* ctx, const void* points_ext_local, const v
 int32_t jj_scalar_mul_sharded_n(jj_ctx* ctx, const void* points_ext_local, const void* scalars32_local,
                                 void* out_all, void* out_local_host, size_t n_total, uint32_t flags);
 
+/* Sum<ExtendedPoint> over a batch spread across the ranks: local jj_point_sum, ncclAllGather of the nranks partial sums
+ * (160 B each), sum of those in rank order; `out` (one point, format per JJ_OUT_*) is the same on every rank.  Device
+ * pointers.  An empty local block contributes the identity. */
+int32_t jj_point_sum_sharded(jj_ctx* ctx, const void* points_ext_local, void* out, size_t n_local, uint32_t flags);
+
 /* Fused compute + all-gather over NVLink peer memory.  Each rank exports its gathered-output buffer
  * (jj_ipc_export -> 64-byte cudaIpcMemHandle), the host exchanges the handles, every rank opens its
  * peers' buffers (jj_ipc_open) and registers the nranks pointers in rank order (own pointer at index

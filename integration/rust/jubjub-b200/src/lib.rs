@@ -135,6 +135,7 @@ extern "C" {
     pub fn jj_comm_destroy(ctx: *mut JjCtx) -> i32;
     pub fn jj_scalar_mul_sharded(ctx: *mut JjCtx, points_ext_local: *const c_void, scalars32_local: *const c_void, out_all: *mut c_void, n_local: usize, flags: u32) -> i32;
     pub fn jj_scalar_mul_sharded_n(ctx: *mut JjCtx, points_ext_local: *const c_void, scalars32_local: *const c_void, out_all: *mut c_void, out_local_host: *mut c_void, n_total: usize, flags: u32) -> i32;
+    pub fn jj_point_sum_sharded(ctx: *mut JjCtx, points_ext_local: *const c_void, out: *mut c_void, n_local: usize, flags: u32) -> i32;
     pub fn jj_ipc_export(ctx: *mut JjCtx, dptr: *const c_void, handle64: *mut c_void) -> i32;
     pub fn jj_ipc_open(ctx: *mut JjCtx, handle64: *const c_void, dptr: *mut *mut c_void) -> i32;
     pub fn jj_ipc_close(ctx: *mut JjCtx, dptr: *mut c_void) -> i32;

@@ -1376,6 +1376,35 @@ int32_t jj_scalar_mul_sharded(jj_ctx* c, const void* points_local, const void* s
     return jj_scalar_mul_sharded_n(c, points_local, scalars_local, out_all, nullptr, n_local * (size_t)c->nranks, flags);
 }
 
+// Sum over a batch that is spread over the ranks: every rank sums its own points (jj_point_sum), the G partial sums
+// (160 B each) are all-gathered and every rank adds them up in rank order -- the one step of this engine where ranks
+// really exchange data they need for their result.  out: one ExtendedPoint (or JJ_OUT_AFFINE / JJ_OUT_BYTES), the same on
+// every rank.
+int32_t jj_point_sum_sharded(jj_ctx* c, const void* points_local, void* out, size_t n_local, uint32_t flags) {
+    if (!c || !out) return JJ_ERR_INVALID_ARG;
+    if (!(flags & JJ_DEVICE_PTRS)) return fail(c, JJ_ERR_INVALID_ARG, "jj_point_sum_sharded takes device pointers");
+    CU(c, cudaSetDevice(c->device));
+    if (c->nranks > 1 && !c->nccl_comm) return fail(c, JJ_ERR_NCCL, "jj_comm_init was not called");
+    if (!c->barrier_word) {
+        CU(c, cudaMalloc((void**)&c->barrier_word, 256));
+        CU(c, cudaMemset(c->barrier_word, 0, 256));
+    }
+    int32_t rc = ensure(c, &c->tmp2, &c->tmp2_cap, (size_t)(c->nranks + 1) * 160 + 64);
+    if (rc) return rc;
+    char* partials = c->tmp2;  // nranks x 160 B, this rank's at index rank
+    rc = jj_point_sum(c, points_local, partials + (size_t)c->rank * 160, 1, n_local, JJ_DEVICE_PTRS | JJ_ASYNC);
+    if (rc) return rc;
+    if (c->nranks > 1) {
+        int nrc = g_nccl.AllGather(partials + (size_t)c->rank * 160, partials, 160, /*ncclInt8*/ 0, c->nccl_comm, c->stream);
+        if (nrc != 0) return nccl_fail(c, "ncclAllGather", nrc);
+    }
+    // the gathered partials are consumed from a second scratch (jj_point_sum uses tmp2 only for host outputs)
+    rc = ensure(c, &c->tmp, &c->tmp_cap, (size_t)c->nranks * 160);
+    if (rc) return rc;
+    CU(c, cudaMemcpyAsync(c->tmp, partials, (size_t)c->nranks * 160, cudaMemcpyDeviceToDevice, c->stream));
+    return jj_point_sum(c, c->tmp, out, 1, (size_t)c->nranks, flags);
+}
+
 int32_t jj_ipc_export(jj_ctx* c, const void* dptr, void* handle64) {
     if (!c || !dptr || !handle64) return JJ_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));

@@ -384,6 +384,15 @@ class Engine:
     def ipc_close(self, ptr):
         self._check(self.lib.jj_ipc_close(self.ctx, ptr))
 
+    def point_sum_sharded(self, points_local, output="extended"):
+        """Sum over a batch spread across the ranks (local sums + all-gather of the partial sums): one point, the same on
+        every rank."""
+        w, dt, f = self._out_fmt(output)
+        o = self._out(True, 1, w, dt)
+        self._check(self.lib.jj_point_sum_sharded(self.ctx, points_local.ptr, o.ptr, points_local.shape[0],
+                                                  f | L.JJ_DEVICE_PTRS))
+        return o
+
     def set_peer_outputs(self, ptrs):
         """Register every rank's gathered-output buffer (rank order; own buffer at index rank) to fuse
         the all-gather into the scalar-mul kernel (P2P stores over NVLink).  None / [] switches back."""

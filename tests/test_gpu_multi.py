@@ -68,6 +68,12 @@ def _worker(rank, world, uid_q, ret, handles, barrier):
     eng.scalar_mul_sharded_vartime(eng.to_device(pts), eng.to_device(k), o)
     ret[(rank, "nccl/legacy")] = o.download()
 
+    # ---- sum over the whole (ragged) batch: local sums + all-gather of the partial sums
+    lo, hi = shard_range(N_RAGGED, rank, world)
+    pts, k = _inputs(ob, lo, hi - lo, M.SEED0 + 2)
+    prod = eng.scalar_mul_vartime(eng.to_device(pts), eng.to_device(k))
+    ret[(rank, "sum")] = eng.point_sum_sharded(prod, output="bytes").download()
+
     # ---- fused gather: P2P stores into every rank's buffer from the kernel, no ncclAllGather
     def register(n_total, output):
         w, dt = fmt[output]
@@ -178,6 +184,17 @@ def test_sharded_all_gather_2gpu(oracle):
         assert (ret[(r, "fused/ext")] == ret[(r, "nccl/ext")]).all()
         assert (ret[(r, "fused/ragged/ext")] == ret[(r, "nccl/ragged/ext")]).all()
     assert checked == WORLD * 14
+    # sum_i [k_i] P_i over the whole ragged batch, computed by both ranks: equal to the oracle's sum of its own results
+    aff, _ = want[N_RAGGED]
+    tot = oracle.affine_to_extended(aff)
+    while len(tot) > 1:
+        if len(tot) % 2:
+            tot = np.concatenate([tot, oracle.identity()])
+        h = len(tot) // 2
+        tot = oracle.ext_add(np.ascontiguousarray(tot[:h]), np.ascontiguousarray(tot[h:]))
+    want_sum = oracle.affine_to_bytes(oracle.batch_normalize(tot))
+    for r in range(WORLD):
+        assert (ret[(r, "sum")] == want_sum).all(), r
     # write-after-read: the consumer of round i must have seen round i's results for EVERY unit of BOTH blocks
     for i in range(WAR_ROUNDS):
         aff, _ = expected(WORLD * N_EQ, 7000 + i)
