@@ -40,12 +40,13 @@ SEED0 = 0x4A55424A55420001
 METRIC = "variable_base_scalar_muls_per_sec"
 UNIT = "scalar-muls/s"
 # algorithmic work per unit: bytes = 160 B point + 32 B scalar in, 160 B point out;
-# IMAD.WIDE.U32 = signed radix-16 window: 252 doublings (4S+3M), 7+~59 additions (8M), 16 M for to_niels,
+# IMAD.WIDE.U32 = signed radix-16 window: 249 doublings (4S+3M; the top part of the scalar starts from a table entry, so the
+# first pass doubles once), 7 table + 1 + ~58 digit additions (8M), 16 M for to_niels,
 # S = 84 and M = 112 multiplier instructions: the minimum of 8x32-bit Montgomery with q's special low limbs.  (The
 # shipped kernels issue S = 91, M = 119 -- one extra multiply per reduction row but the last replaces three ALU
 # instructions -- so the fraction undercounts the pipe's real occupancy; `imads_issued_per_unit` is ncu's count.)
 BYTES_PER_UNIT = 352
-IMADS_PER_UNIT = 252 * (4 * 84 + 3 * 112) + (7 + 63 * 15 / 16) * 8 * 112 + 16 * 112
+IMADS_PER_UNIT = 249 * (4 * 84 + 3 * 112) + (7 + 1 + 62 * 15 / 16) * 8 * 112 + 16 * 112
 # from the committed ncu capture of the dominant kernel at 2^20 units (ncu --set full, one launch):
 # dram__bytes_read.sum + dram__bytes_write.sum, and IMAD.WIDE thread instructions executed per unit (source page)
 NCU_PROFILE = "profiles/r02g_ncu_scalar_mul_default_n1048576.csv"

@@ -6,9 +6,9 @@
 // one scalar-mul and uses a signed radix-16 window:
 //
 //   k (low 252 bits, exactly the bits the reference consumes, src/lib.rs:366-372)
-//     = d63 * 16^63 + sum_{i<63} d_i * 16^i,   d_i in [-8, 7],  d63 in {0, 1}
+//     = T * 16^62 + sum_{i<62} d_i * 16^i,   d_i in [-8, 7],  T in [0, 16]
 //
-// obtained by adding 0x0888...8 to k and reading nibbles (nibble - 8).  A per-scalar-mul
+// obtained by adding 0x0088...8 to k and reading nibbles (nibble - 8) below the top part T.  A per-scalar-mul
 // table holds the eight extended-Niels multiples 1P..8P; negative digits use the
 // reference's own subtraction formula (src/lib.rs:922-940), so no field negation is
 // needed.  Cost: 7 additions + 8 to_niels for the table, then 252 doublings and <= 63
@@ -24,17 +24,18 @@
 
 namespace jj {
 
-// K = ((k mod 2^252) + 0x0888...8) << 3, so that bit 255 of K is d63 and, after one more
-// left shift, the top nibble is digit 62.
-JJ_DEVICE void recode_scalar(uint32_t K[8], const uint32_t k[8]) {
+// t = (k mod 2^252) + 0x0088...8 (an 8 in each of the nibbles 0..61).  Nibble i < 62 of t, minus 8, is the signed digit d_i;
+// the top byte of t is T = (nibble 62 of k) + carry in [0, 16].  Returns T and K = t << 8, whose top nibble is digit 61.
+JJ_DEVICE uint32_t recode_scalar(uint32_t K[8], const uint32_t k[8]) {
     uint32_t t[8];
     add_cc(t[0], k[0], 0x88888888u);
 #pragma unroll
     for (int i = 1; i < 7; i++) addc_cc(t[i], k[i], 0x88888888u);
-    addc(t[7], k[7] & 0x0fffffffu, 0x08888888u);
+    addc(t[7], k[7] & 0x0fffffffu, 0x00888888u);
 #pragma unroll
-    for (int i = 7; i > 0; i--) K[i] = (t[i] << 3) | (t[i - 1] >> 29);
-    K[0] = t[0] << 3;
+    for (int i = 7; i > 0; i--) K[i] = (t[i] << 8) | (t[i - 1] >> 24);
+    K[0] = t[0] << 8;
+    return t[7] >> 24;
 }
 JJ_DEVICE void shl_256(uint32_t K[8], int s) {  // 0 < s < 32
 #pragma unroll
@@ -104,25 +105,40 @@ JJ_DEVICE void scalar_mul_core(ext_point& acc, const ext_point& P, const uint32_
         }
     }
     uint32_t K[8];
-    recode_scalar(K, k);
+    const uint32_t T = recode_scalar(K, k);
+    // k = T * 16^62 + sum_{i < 62} d_i 16^i.  The top part T = 2h + b, h in [0, 8]: start from [h]P read back from the table
+    // (Niels (v+u, v-u, z) -> (2u : 2v : 2z), the same point), and let the first pass of the loop be ONE doubling and the
+    // addition of [b]P instead of four doublings of "P or identity" and the addition of digit 62: three doublings fewer per
+    // scalar multiplication.
     {
-        // acc = d63 ? P : identity
-        ext_point id;
-        point_set_identity(id);
-        bool top = (K[7] >> 31) != 0;
-        fe_select(acc.u, id.u, P.u, top);
-        fe_select(acc.v, id.v, P.v, top);
-        fe_select(acc.z, id.z, P.z, top);
-        fe_select(acc.t1, id.t1, P.t1, top);
-        fe_select(acc.t2, id.t2, P.t2, top);
-        shl_256(K, 1);
+        ext_niels n;
+        const int h = (int)(T >> 1);
+        if (CT) {
+            table_scan(n, tbl, h);
+        } else {
+            fe_set_one<FqP>(n.vpu);
+            fe_set_one<FqP>(n.vmu);
+            fe_set_one<FqP>(n.z);
+            if (h != 0) tbl.load(h - 1, n);
+        }
+        fe_sub<FqP>(acc.u, n.vpu, n.vmu);
+        fe_add<FqP>(acc.v, n.vpu, n.vmu);
+        fe_dbl<FqP>(acc.z, n.z);
+        acc.t1 = acc.u;  // not read before the next addition: every doubling recomputes t1, t2
+        acc.t2 = acc.v;
     }
 #pragma unroll 1
     for (int i = 62; i >= 0; i--) {
+        const int nd = i == 62 ? 1 : 4;
 #pragma unroll kDoubleUnroll
-        for (int j = 0; j < 4; j++) point_double(acc, acc);
-        int d = (int)(K[7] >> 28) - 8;
-        shl_256(K, 4);
+        for (int j = 0; j < nd; j++) point_double(acc, acc);
+        int d;
+        if (i == 62) {
+            d = (int)(T & 1u);
+        } else {
+            d = (int)(K[7] >> 28) - 8;
+            shl_256(K, 4);
+        }
         if (CT) {
             ext_niels n;
             table_scan(n, tbl, d < 0 ? -d : d);

@@ -18,6 +18,19 @@
 
 namespace jj {
 
+// Round 1's recoding, kept for this experimental mapping: K = ((k mod 2^252) + 0x0888...8) << 3, so that bit 255 of K is the top
+// carry d63 and, after one more left shift, the top nibble is digit 62 (all 63 digits signed, four doublings in every pass).
+JJ_DEVICE void recode_scalar_r1(uint32_t K[8], const uint32_t k[8]) {
+    uint32_t t[8];
+    add_cc(t[0], k[0], 0x88888888u);
+#pragma unroll
+    for (int i = 1; i < 7; i++) addc_cc(t[i], k[i], 0x88888888u);
+    addc(t[7], k[7] & 0x0fffffffu, 0x08888888u);
+#pragma unroll
+    for (int i = 7; i > 0; i--) K[i] = (t[i] << 3) | (t[i - 1] >> 29);
+    K[0] = t[0] << 3;
+}
+
 #if defined(JJ_HOST_EMUL)
 // host emulation: one thread's slot file is a plain array of 8-word slots
 struct SlotFile {
@@ -162,7 +175,7 @@ JJ_DEVICE void scalar_mul_slots(SlotFile S, const uint32_t k[8], Table& tbl) {
         tbl.store(j, nj);
     }
     uint32_t K[8];
-    recode_scalar(K, k);
+    recode_scalar_r1(K, k);
     {
         ext_point id;
         point_set_identity(id);
