@@ -49,9 +49,9 @@ BYTES_PER_UNIT = 352
 IMADS_PER_UNIT = 249 * (4 * 84 + 3 * 112) + (7 + 1 + 62 * 15 / 16) * 8 * 112 + 16 * 112
 # from the committed ncu capture of the dominant kernel at 2^20 units (ncu --set full, one launch):
 # dram__bytes_read.sum + dram__bytes_write.sum, and IMAD.WIDE thread instructions executed per unit (source page)
-NCU_PROFILE = "profiles/r02g_ncu_scalar_mul_default_n1048576.csv"
-NCU_DRAM_BYTES_PER_LAUNCH = 225.80e6 + 758.71e6
-NCU_IMADS_ISSUED_PER_UNIT = 246637
+NCU_PROFILE = "profiles/r02o_ncu_scalar_mul_default_n1048576.csv"
+NCU_DRAM_BYTES_PER_LAUNCH = 226.49e6 + 653.64e6
+NCU_IMADS_ISSUED_PER_UNIT = 243955
 GEN_RAW = np.array([[0xE4B3D35DF1A7ADFE, 0xCAF55D1B29BF81AF, 0x8B0F03DDD60A8187, 0x62EDCBB8BF3787C8, 0xB, 0, 0, 0]],
                    dtype=np.uint64)
 
