@@ -678,7 +678,9 @@ JJ_DEVICE bool fe_is_canonical(const fe& v) {
     return borrow != 0;
 }
 
-// r = a^e for a constant exponent (EXP::word(i), EXP::NW 32-bit words): 4-bit fixed window.
+// r = a^e for a constant exponent (EXP::word(i), EXP::NW 32-bit words): 4-bit fixed window.  The exponent is the same for
+// every lane, so its zero digits are skipped by a warp-uniform branch and the squarings of the leading one are not run
+// (the accumulator starts at the first non-zero digit's table entry).
 template <class F, class EXP>
 JJ_DEVICE void fe_pow_const(fe& r, const fe& a) {
     fe tbl[16];
@@ -688,17 +690,25 @@ JJ_DEVICE void fe_pow_const(fe& r, const fe& a) {
     for (int i = 2; i < 16; i++) mont_mul<F>(tbl[i], tbl[i - 1], a);
     fe acc;
     fe_set_one<F>(acc);
+    bool started = false;
 #pragma unroll 1
     for (int wi = EXP::NW - 1; wi >= 0; wi--) {
         uint32_t e = EXP::word(wi);
 #pragma unroll 1
         for (int s = 28; s >= 0; s -= 4) {
+            const uint32_t d = (e >> s) & 15u;
+            if (!started) {
+                if (d) {
+                    acc = tbl[d];
+                    started = true;
+                }
+                continue;
+            }
             mont_sqr<F>(acc, acc);
             mont_sqr<F>(acc, acc);
             mont_sqr<F>(acc, acc);
             mont_sqr<F>(acc, acc);
-            uint32_t d = (e >> s) & 15u;
-            mont_mul<F>(acc, acc, tbl[d]);
+            if (d) mont_mul<F>(acc, acc, tbl[d]);
         }
     }
     r = acc;

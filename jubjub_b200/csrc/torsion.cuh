@@ -91,17 +91,25 @@ JJ_DEVICE void fq_pow_const_shared(fe& r, const fe& a) {
     for (int i = 2; i < 16; i++) fq_mul(tbl[i], tbl[i - 1], a);
     fe acc;
     fe_set_one<FqP>(acc);
+    bool started = false;  // the exponent is warp-uniform: leading zeros and zero digits are skipped (fe_pow_const)
 #pragma unroll 1
     for (int wi = EXP::NW - 1; wi >= 0; wi--) {
         uint32_t e = EXP::word(wi);
 #pragma unroll 1
         for (int s = 28; s >= 0; s -= 4) {
+            const uint32_t d = (e >> s) & 15u;
+            if (!started) {
+                if (d) {
+                    acc = tbl[d];
+                    started = true;
+                }
+                continue;
+            }
             fq_sqr(acc, acc);
             fq_sqr(acc, acc);
             fq_sqr(acc, acc);
             fq_sqr(acc, acc);
-            uint32_t d = (e >> s) & 15u;
-            fq_mul(acc, acc, tbl[d]);
+            if (d) fq_mul(acc, acc, tbl[d]);
         }
     }
     r = acc;
