@@ -179,7 +179,9 @@ int32_t jj_affine_to_niels(jj_ctx* ctx, const void* p_affine, void* out_aniels, 
 /* out[i] = [scalars[i]] points[i]: `&ExtendedPoint * &Fr` src/lib.rs:873-879 ->
  * ExtendedPoint::multiply :830-833 -> ExtendedNielsPoint::multiply :356-379.
  * Output: ExtendedPoint (projectively equal to the reference's, affine-identical), or with
- * JJ_OUT_AFFINE / JJ_OUT_BYTES the normalised point / its encoding (bit-exact). */
+ * JJ_OUT_AFFINE / JJ_OUT_BYTES the normalised point / its encoding (bit-exact).
+ * Variable-time in the scalars by default (signed radix-16 windows, zero digits skipped); with JJ_CONST_TIME no branch and no
+ * memory address depends on the scalars (about 4 % slower): the mode that keeps the reference's policy (src/lib.rs:12-17). */
 int32_t jj_scalar_mul(jj_ctx* ctx, const void* points_ext, const void* scalars32, void* out, size_t n, uint32_t flags);
 /* Wire format in: points32[i] is the 32-byte encoding of an AffinePoint (src/lib.rs:455-464).  Decodes on the
  * device exactly as jj_batch_from_bytes (ZIP-216 rule unless JJ_PRE_ZIP216), multiplies by scalars32[i] and writes
