@@ -83,7 +83,7 @@ def loops(insns):
     out = []
     for addr, op, args in insns:
         if op.startswith("BRA") and not op.startswith("BRA.U"):
-            m = re.search(r"0x([0-9a-f]+)", args)
+            m = re.search(r"0x([0-9a-f]+)", args)  # also the `BRA P3, 0x...` form
             if m and int(m.group(1), 16) < addr:
                 out.append((int(m.group(1), 16), addr))
     return sorted(out, key=lambda r: r[1] - r[0])

@@ -389,11 +389,12 @@ def test_types_star_import_and_vartime_gate():
 
 
 def test_constant_time_kernel_has_no_scalar_dependent_branch(built):
-    """Structural check of JJ_CONST_TIME on the shipped SASS: inside the window loop of the constant-time kernel the only
-    control flow is the three loop back-edges (4 doublings, 8-entry table scan, 63 windows) and the calls of the shared
-    Fq product -- no BSSY / BSYNC reconvergence pair, i.e. no divergent branch on the digit -- and the table loads sit in
-    the scan loop (4 per iteration), not behind a digit-indexed address.  The variable-time kernel, for contrast, has the
-    divergent `if (digit != 0)`."""
+    """Structural check of JJ_CONST_TIME on the shipped SASS: inside the window loop of the constant-time kernel there are
+    exactly three loop back-edges (doublings, 8-entry table scan, 63 windows), the calls of the shared Fq product, and
+    no BSSY / BSYNC reconvergence pair -- ptxas brackets every branch that may diverge with one, so the only other
+    branches left are warp-uniform ones on the (public) loop counter: the first pass doubles once and takes its digit from
+    the top part of the scalar by a select.  The table loads sit in the scan loop (4 per iteration), not behind a
+    digit-indexed address.  The variable-time kernel, for contrast, has the divergent `if (digit != 0)`."""
     import subprocess
 
     from jubjub_b200 import _lib
@@ -413,7 +414,7 @@ def test_constant_time_kernel_has_no_scalar_dependent_branch(built):
         (ins,) = [v for k, v in funcs.items() if name_part in k]
         back = []
         for a, t in ins:
-            m = re.match(r"(?:@!?U?P\d+\s+)?BRA\s+0x([0-9a-f]+)", t)
+            m = re.match(r"(?:@!?U?P\d+\s+)?BRA\s+(?:!?P\d+,\s*)?0x([0-9a-f]+)", t)
             if m and int(m.group(1), 16) < a:
                 back.append((int(m.group(1), 16), a))
         # the window loop: the innermost loop that contains the 8 calls of one addition
@@ -427,8 +428,8 @@ def test_constant_time_kernel_has_no_scalar_dependent_branch(built):
     ct, ct_back = window_loop("k_scalar_mulILi512ELi1ELi1ELb0ELb1")
     vt, _ = window_loop("k_scalar_mulILi512ELi1ELi1ELb0ELb0")
     assert not any(re.search(r"\b(BSSY|BSYNC|WARPSYNC)\b", t) for _, t in ct)
-    bras = [t for _, t in ct if re.search(r"\bBRA\b", t)]
-    assert len(bras) == 3 and len(ct_back) == 3, bras          # doubling loop, scan loop, window loop: back-edges only
+    assert len(ct_back) == 3, ct_back                           # doubling loop, scan loop, window loop
+    assert sum(1 for _, t in ct if re.search(r"\bBRA\b", t)) <= 5   # + at most two uniform forward branches on the counter
     scan = min((r for r in ct_back), key=lambda r: r[1] - r[0])
     loads = [(a, t) for a, t in ct if "LDG" in t]
     assert len(loads) == 4 and all(scan[0] <= a <= scan[1] for a, _ in loads)
