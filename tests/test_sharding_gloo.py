@@ -76,3 +76,62 @@ def test_shard_range_properties():
         equal_shards(10, 4)
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def _worker_ragged(rank, world, port, n, ret):
+    """The ragged gather (one broadcast per rank's block, jj_scalar_mul_sharded_n's grouped ncclBroadcast) and the sharded
+    sum (local sums, all-gather of the partial sums, sum in rank order: jj_point_sum_sharded), mirrored with gloo."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jubjub_b200.sharding import shard_range
+    from oracle import binding as ob
+    from oracle import model as M
+
+    lo, hi = shard_range(n, rank, world)
+    cnt = hi - lo
+    g = ob.affine_to_extended(ob.generator())
+    t = ob.fe_to_bytes(ob.FR, ob.fe_stream(ob.FR, M.SEED0 + 3, cnt, first=lo))
+    k = ob.fe_to_bytes(ob.FR, ob.fe_stream(ob.FR, M.SEED0 + 2, cnt, first=lo))
+    mine = ob.scalar_mul(ob.scalar_mul(np.repeat(g, cnt, axis=0), t, 1), k, 1)
+    out = torch.zeros((n, 20), dtype=torch.int64)
+    out[lo:hi] = torch.from_numpy(mine.view(np.int64))
+    for r in range(world):  # every rank's block travels from its owner, in place
+        a, b = shard_range(n, r, world)
+        if b > a:
+            blk = out[a:b].contiguous()
+            dist.broadcast(blk, src=r)
+            out[a:b] = blk
+    # sharded sum: local sum -> all-gather of one point per rank -> sum in rank order
+    def fold(p):
+        acc = ob.identity()
+        for i in range(len(p)):
+            acc = ob.ext_add(acc, np.ascontiguousarray(p[i:i + 1]))
+        return acc
+    partial = torch.from_numpy(fold(mine).view(np.int64))
+    partials = torch.empty((world, 20), dtype=torch.int64)
+    dist.all_gather_into_tensor(partials, partial)
+    total = fold(partials.numpy().view(np.uint64))
+    ret[rank] = (out.numpy().view(np.uint64).copy(), ob.batch_normalize(total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_gather_and_sharded_sum_world2(oracle):
+    from oracle import model as M
+
+    n, world = 25, 2  # blocks of 12 and 13
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_ragged, args=(world, _free_port(), n, ret), nprocs=world, join=True)
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(1, oracle.fe_stream(1, M.SEED0 + 3, n))
+    k = oracle.fe_to_bytes(1, oracle.fe_stream(1, M.SEED0 + 2, n))
+    want = oracle.scalar_mul(oracle.scalar_mul(np.repeat(g, n, axis=0), t), k)
+    acc = oracle.identity()
+    for i in range(n):
+        acc = oracle.ext_add(acc, np.ascontiguousarray(want[i:i + 1]))
+    for r in range(world):
+        out, total = ret[r]
+        assert (out == want).all(), r                                  # every rank holds the whole batch in index order
+        assert (total == oracle.batch_normalize(acc)).all(), r        # and the same sum, equal to the single-process fold
