@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--what", default="smul", choices=["smul", "fixed", "fqmul", "torsion"])
+    ap.add_argument("--ct", action="store_true", help="constant-time mode (JJ_CONST_TIME)")
     a = ap.parse_args()
     eng = jj.Engine(0)
     n = 1 << a.logn
@@ -50,7 +51,7 @@ def main():
     o = eng.empty((n, 20))
     for _ in range(a.reps):
         eng.timer_start()
-        eng.scalar_mul_vartime(pts, k, out=o, flags=jj.JJ_ASYNC)
+        (eng.scalar_mul if a.ct else eng.scalar_mul_vartime)(pts, k, out=o, flags=jj.JJ_ASYNC)
         ms = eng.timer_stop()
         print(f"n={n} variant={a.variant}: {ms:.3f} ms  {n / ms * 1e3:.4e}/s")
 
