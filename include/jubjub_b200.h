@@ -88,7 +88,9 @@ const char* jj_last_error(const jj_ctx* ctx);
 const char* jj_version(void);
 int32_t jj_device_info(jj_ctx* ctx, int32_t* sm_count, int32_t* sm_clock_khz, uint64_t* hbm_bytes);
 /* Tuning knob; 0 = library defaults.  13 / 24 / 5: variable-base kernel with 16 / 24 / 8 warps
- * per SM; 100: fixed-base kernel with 4-bit windows; 200 / 201: converted outputs (JJ_OUT_AFFINE / JJ_OUT_BYTES) of
+ * per SM; fixed-base table: default 12-bit windows (4.1 MB in global memory, 22 additions per scalar-mul), 116: 16-bit windows
+ * (50 MB, 17 additions: for bases that live long enough to pay the 18 ms table build), 107 / 100: 7- / 4-bit windows in shared
+ * memory (216 KB TMA-staged / 47 KB); 200 / 201: converted outputs (JJ_OUT_AFFINE / JJ_OUT_BYTES) of
  * device-resident variable-base batches always / never use the kernel's fused normalise epilogue (default: only for the
  * fused all-gather, where it shrinks the peer stores to 32 bytes; on one GPU the separate pass is 1 % faster). */
 int32_t jj_set_scalar_mul_variant(jj_ctx* ctx, int32_t variant);
@@ -192,7 +194,8 @@ int32_t jj_scalar_mul_encoded(jj_ctx* ctx, const void* points32, const void* sca
                               uint32_t flags);
 
 /* out[i] = [scalars[i]] base: `&AffinePoint * &Fr` src/lib.rs:1109-1115 -> AffineNielsPoint::multiply :271-295,
- * one shared base; the per-window AffineNiels table is built once per base and cached in ctx. */
+ * one shared base; the per-window AffineNiels table (no doublings: one mixed addition per window) is built on the device
+ * once per base and cached in ctx -- the first call with a new base pays for it (5 ms for the default 12-bit windows). */
 int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* scalars32, void* out, size_t n, uint32_t flags);
 /* Sum<ExtendedPoint> src/lib.rs:183-193 (`iter.fold(identity, |acc, p| acc + p)`; SubgroupPoint :1161-1171), batched: the
  * input holds `groups` consecutive groups of `group_size` points, out[j] = sum of group j (groups = 1: one sum of the

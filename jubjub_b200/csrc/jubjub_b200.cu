@@ -103,7 +103,8 @@ struct jj_ctx {
     int live_graphs = 0;  // graphs captured on this context and not yet destroyed: their nodes hold scratch pointers
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[kStages] = {nullptr, nullptr};
-    uint32_t* fixed_table = nullptr;  // 64*8*24 words
+    uint32_t* fixed_table = nullptr;  // fixed-base window table of the cached base (FixedGeom<fixed_w>)
+    size_t fixed_table_cap = 0;
     char* fixed_base_dev = nullptr;   // 64 B
     char fixed_base_key[64];
     bool fixed_valid = false;
@@ -195,7 +196,10 @@ const SmulVariant kVariants[] = {
 };
 constexpr int kDefaultVariant = 13;
 // knob values outside the mapping table
-constexpr int kFixedW4 = 100;         // fixed-base kernel with 4-bit windows (47 KB table)
+constexpr int kFixedW4 = 100;         // fixed-base kernel with 4-bit windows (47 KB table in shared memory)
+constexpr int kFixedW7 = 107;         // fixed-base kernel with 7-bit windows (216 KB table in shared memory, TMA-staged)
+constexpr int kFixedW16 = 116;        // fixed-base kernel with 16-bit windows (50 MB table in global memory: for long-lived bases)
+constexpr int kFixedWide = 12;        // default: 12-bit windows, 4.1 MB table in global memory (L2 / L1 resident)
 constexpr int kFusedNormOn = 200;     // converted outputs: always use the fused normalise epilogue (k_scalar_mul<.., NORM>)
 constexpr int kFusedNormOff = 201;    // ... never (separate k_batch_normalize pass)
 
@@ -568,7 +572,12 @@ int wire_rounds() {
 
 
 // fixed-base window width: 7 (216 KB table, the default) or 4 (47 KB table, variant 100)
-int fixed_w(const jj_ctx* c) { return c->smul_variant == kFixedW4 ? 4 : 7; }
+int fixed_w(const jj_ctx* c) {
+    return c->smul_variant == kFixedW4 ? 4 : c->smul_variant == kFixedW7 ? 7 : c->smul_variant == kFixedW16 ? 16 : kFixedWide;
+}
+size_t fixed_table_bytes(int w) {
+    return w == 4 ? FixedGeom<4>::BYTES : w == 7 ? FixedGeom<7>::BYTES : w == 16 ? FixedGeom<16>::BYTES : FixedGeom<kFixedWide>::BYTES;
+}
 
 int32_t build_fixed_table(jj_ctx* c, const void* base_affine, uint32_t flags) {
     if (capturing(c))
@@ -580,17 +589,31 @@ int32_t build_fixed_table(jj_ctx* c, const void* base_affine, uint32_t flags) {
         memcpy(key, base_affine, 64);
     const int w = fixed_w(c);
     if (c->fixed_valid && c->fixed_w == w && memcmp(key, c->fixed_base_key, 64) == 0) return JJ_OK;
-    if (!c->fixed_table) CU(c, cudaMalloc((void**)&c->fixed_table, FixedGeom<7>::BYTES));
+    if (c->fixed_table && c->fixed_table_cap < fixed_table_bytes(w)) {
+        CU(c, cudaFree(c->fixed_table));
+        c->fixed_table = nullptr;
+        c->fixed_valid = false;
+    }
+    if (!c->fixed_table) {
+        CU(c, cudaMalloc((void**)&c->fixed_table, fixed_table_bytes(w)));
+        c->fixed_table_cap = fixed_table_bytes(w);
+    }
     if (!c->fixed_base_dev) CU(c, cudaMalloc((void**)&c->fixed_base_dev, 64));
     CU(c, cudaMemcpy(c->fixed_base_dev, key, 64, cudaMemcpyHostToDevice));
-    const int entries = w == 4 ? FixedGeom<4>::ENTRIES : FixedGeom<7>::ENTRIES;
-    const int blocks = (entries + 63) / 64;
+    const int entries = w == 4 ? FixedGeom<4>::ENTRIES : w == 7 ? FixedGeom<7>::ENTRIES : w == 16 ? FixedGeom<16>::ENTRIES
+                                                                                                   : FixedGeom<kFixedWide>::ENTRIES;
+    // one thread per entry up to 8 blocks of 64 threads per SM (the kernel grid-strides over larger tables)
+    const int blocks = std::min((entries + 63) / 64, c->sm_count * 8);
     int32_t rc = ensure(c, &c->tbl, &c->tbl_cap, (size_t)(blocks * 2) * 32768);
     if (rc) return rc;
     if (w == 4)
         k_fixed_table_build<4><<<blocks, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
-    else
+    else if (w == 7)
         k_fixed_table_build<7><<<blocks, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
+    else if (w == 16)
+        k_fixed_table_build<16><<<blocks, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
+    else
+        k_fixed_table_build<kFixedWide><<<blocks, 64, 0, c->stream>>>(c->fixed_base_dev, c->fixed_table, c->tbl);
     c->launches++;
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));
@@ -608,6 +631,15 @@ int32_t launch_fixed(jj_ctx* c, cudaStream_t s, const char* scalars, char* dst, 
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
     const int per_sm = smem > 100000 ? 1 : 2;
     kern<<<grid_for(c, cnt, T, per_sm), T, smem, s>>>(c->fixed_table, scalars, dst, cnt, smont);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return JJ_OK;
+}
+
+template <int W>
+int32_t launch_fixed_wide(jj_ctx* c, cudaStream_t s, const char* scalars, char* dst, size_t cnt, bool smont) {
+    constexpr int T = 512;
+    k_scalar_mul_fixed_gmem<T, W><<<grid_for(c, cnt, T, 1), T, 0, s>>>(c->fixed_table, scalars, dst, cnt, smont);
     c->launches++;
     CU(c, cudaGetLastError());
     return JJ_OK;
@@ -722,7 +754,7 @@ const char* jj_last_error(const jj_ctx* c) { return c ? c->err : "null context";
 uint64_t jj_launch_count(const jj_ctx* c) { return c ? c->launches : 0; }
 int32_t jj_set_scalar_mul_variant(jj_ctx* c, int32_t v) {
     if (!c) return JJ_ERR_INVALID_ARG;
-    bool known = v == 0 || v == kFixedW4 || v == kFusedNormOn || v == kFusedNormOff;
+    bool known = v == 0 || v == kFixedW4 || v == kFixedW7 || v == kFixedW16 || v == kFusedNormOn || v == kFusedNormOff;
     for (const SmulVariant& k : kVariants) known = known || k.id == v;
     if (!known) return fail(c, JJ_ERR_INVALID_ARG, "unknown scalar-mul variant %d (experimental mappings need a -DJJ_EXPERIMENTS build)", v);
     c->smul_variant = v;
@@ -1117,8 +1149,11 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
             if (rc) return rc;
             dst = *tmp;
         }
-        int32_t rc = fixed_w(c) == 4 ? launch_fixed<256, 4, false>(c, s, din[0], dst, cnt, smont)
-                                     : launch_fixed<512, 7, true>(c, s, din[0], dst, cnt, smont);
+        const int w = fixed_w(c);
+        int32_t rc = w == 4   ? launch_fixed<256, 4, false>(c, s, din[0], dst, cnt, smont)
+                     : w == 7 ? launch_fixed<512, 7, true>(c, s, din[0], dst, cnt, smont)
+                     : w == 16 ? launch_fixed_wide<16>(c, s, din[0], dst, cnt, smont)
+                               : launch_fixed_wide<kFixedWide>(c, s, din[0], dst, cnt, smont);
         if (rc || unit == 160) return rc;
         return normalize_launch(c, s, dst, dout[0], cnt, unit, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap, !S);
     });

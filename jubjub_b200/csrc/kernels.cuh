@@ -602,44 +602,48 @@ template <int W>
 __global__ void __launch_bounds__(64) k_fixed_table_build(const char* __restrict__ base_affine,
                                                           uint32_t* __restrict__ table, char* __restrict__ scratch) {
     using G = FixedGeom<W>;
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= G::ENTRIES) return;
-    const bool top = e == G::NW * G::PER;
-    int i = top ? G::NW - 1 : e / G::PER, j = top ? 0 : e % G::PER;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     aff_point B;
     ld_fe(B.u, base_affine);
     ld_fe(B.v, base_affine + 32);
-    ext_point P, acc;
-    point_from_affine(P, B);
-    fe k;
-    fe_set_zero(k);
-    {   // k = (j + 1) << (W * i); spans at most two words
-        const int bit = W * i;
-        uint64_t v = (uint64_t)(j + 1) << (bit & 31);
+    // grid-stride over the entries: the window-table scratch (1 KB per thread) is sized by the grid, not by the table
+    for (int e = tid; e < G::ENTRIES; e += nthreads) {
+        const bool top = e == G::NW * G::PER;
+        int i = top ? G::NW - 1 : e / G::PER, j = top ? 0 : e % G::PER;
+        ext_point P, acc;
+        point_from_affine(P, B);
+        fe k;
+        fe_set_zero(k);
+        const int extra = (!top && i == G::NW - 1) ? G::EXCESS : 0;  // doublings owed by the top window (FixedGeom)
+        {   // k = (j + 1) << (W * i - extra); spans at most two words
+            const int bit = W * i - extra;
+            uint64_t v = (uint64_t)(j + 1) << (bit & 31);
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                if (w == (bit >> 5)) k.w[w] = (uint32_t)v;
+                if (w == (bit >> 5) + 1) k.w[w] = (uint32_t)(v >> 32);
+            }
+        }
+        size_t gwarp = (size_t)tid >> 5;
+        GmemTable t{scratch + gwarp * 32768 + (tid & 31) * 32};
+        scalar_mul_core(acc, P, k.w, t);
+        const int dbl = top ? W : extra;
+#pragma unroll 1
+        for (int d = 0; d < dbl; d++) point_double(acc, acc);
+        fe zi;
+        fe_invert<FqP>(zi, acc.z);
+        aff_point a;
+        aff_niels nn;
+        mont_mul<FqP>(a.u, acc.u, zi);
+        mont_mul<FqP>(a.v, acc.v, zi);
+        affine_to_niels(nn, a);
+        uint32_t* dst = table + (size_t)e * 24;
 #pragma unroll
         for (int w = 0; w < 8; w++) {
-            if (w == (bit >> 5)) k.w[w] = (uint32_t)v;
-            if (w == (bit >> 5) + 1) k.w[w] = (uint32_t)(v >> 32);
+            dst[w] = nn.vpu.w[w];
+            dst[8 + w] = nn.vmu.w[w];
+            dst[16 + w] = nn.t2d.w[w];
         }
-    }
-    size_t gwarp = (size_t)e >> 5;
-    GmemTable t{scratch + gwarp * 32768 + (e & 31) * 32};
-    scalar_mul_core(acc, P, k.w, t);
-    if (top)
-        for (int d = 0; d < W; d++) point_double(acc, acc);
-    fe zi;
-    fe_invert<FqP>(zi, acc.z);
-    aff_point a;
-    aff_niels nn;
-    mont_mul<FqP>(a.u, acc.u, zi);
-    mont_mul<FqP>(a.v, acc.v, zi);
-    affine_to_niels(nn, a);
-    uint32_t* dst = table + (size_t)e * 24;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        dst[w] = nn.vpu.w[w];
-        dst[8 + w] = nn.vmu.w[w];
-        dst[16 + w] = nn.t2d.w[w];
     }
 }
 
@@ -696,6 +700,42 @@ __global__ void __launch_bounds__(THREADS)
         st_ext(out, i, acc);
     }
     if (!staged) mbar_wait(&mbar, 0);  // never leave the block while the bulk copy is in flight
+}
+
+// Fixed-base multiplication with WIDE windows: the table stays in global memory.  With W = 12 it is 21 windows x 2 048
+// entries x 96 B = 4.1 MB -- L2-resident and, because the warps of an SM walk the windows nearly in step, mostly L1-resident
+// (one window's sub-table is 196 KB) -- and a scalar-mul is 22 mixed additions instead of the 37 of the 7-bit table that
+// fits shared memory.  Entries are read with three 256-bit non-coherent loads (LDG.E.256.CONSTANT).
+struct fixed_table_gview {
+    const char* base;  // [entry][96 bytes]
+    __device__ __forceinline__ void ld(fe& r, const char* p) const {
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                       "=r"(r.w[7])
+                     : "l"(p));
+    }
+    __device__ __forceinline__ void load_signed(int entry, bool neg, aff_niels& n) const {
+        const char* p = base + (size_t)entry * 96;
+        const int o = neg ? 32 : 0;
+        ld(n.vpu, p + o);
+        ld(n.vmu, p + 32 - o);
+        ld(n.t2d, p + 64);
+    }
+};
+template <int THREADS, int W>
+__global__ void __launch_bounds__(THREADS)
+    k_scalar_mul_fixed_gmem(const uint32_t* __restrict__ table, const char* __restrict__ scalars, char* __restrict__ out,
+                            size_t n, bool scalar_mont) {
+    fixed_table_gview view{(const char*)table};
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+        fe k;
+        ext_point acc;
+        ld_fe(k, scalars + i * 32);
+        if (scalar_mont) fe_to_canonical<FrP>(k, k);
+        scalar_mul_fixed_core<W, true>(acc, k.w, view);
+        st_ext(out, i, acc);
+    }
 }
 
 // ---- normalisation / encoding -------------------------------------------------------------------

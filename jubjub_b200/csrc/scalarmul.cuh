@@ -235,10 +235,15 @@ JJ_DEVICE void scalar_mul_wnaf_core(ext_point& acc, const ext_point& P, const Na
 // entries x 96 B = 216 KB, the whole shared memory of an SM; W = 4: 63 windows, 47 KB.
 template <int W>
 struct FixedGeom {
+    static_assert(W >= 2 && W <= 16 && W * ((252 + W - 1) / W) <= 256, "the recoding needs W * NW <= 256 (W = 4, 7, 12, 14, 16 ...)");
     static constexpr int NW = (252 + W - 1) / W;
     static constexpr int PER = 1 << (W - 1);
     static constexpr int ENTRIES = NW * PER + 1;
     static constexpr uint32_t BYTES = (uint32_t)ENTRIES * 96u;
+    // When W * NW > 252 (W = 16) the top window's multiples (j+1) * 2^(W (NW-1)) can reach 2^252 and beyond, which the
+    // 252-bit scalar-mul core cannot take as a scalar: the table builders multiply by (j+1) * 2^(W (NW-1) - EXCESS) and
+    // double EXCESS times.  (A digit of the top window never exceeds 2^(252 - W (NW-1)) + 1, but the table is complete.)
+    static constexpr int EXCESS = W * NW > 252 ? W * NW - 252 : 0;
 };
 struct fixed_table_view {
     const uint32_t* base;  // [entry][24 words]
@@ -279,8 +284,8 @@ JJ_DEVICE void recode_fixed(uint32_t t[8], const uint32_t k[8]) {
     for (int i = 1; i < 7; i++) addc_cc(t[i], k[i], c[i]);
     addc(t[7], k[7] & 0x0fffffffu, c[7]);
 }
-template <int W, bool INL>
-JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const fixed_table_view& tbl) {
+template <int W, bool INL, class View = fixed_table_view>
+JJ_DEVICE void scalar_mul_fixed_core(ext_point& acc, const uint32_t k[8], const View& tbl) {
     constexpr int NW = FixedGeom<W>::NW, PER = FixedGeom<W>::PER;
     uint32_t t[8];
     recode_fixed<W>(t, k);

@@ -107,15 +107,15 @@ static void fixed_table(const void* base_affine, uint32_t* table, int first, int
         const bool top = e == G::NW * G::PER;
         int i = top ? G::NW - 1 : e / G::PER, j = top ? 0 : e % G::PER;
         uint32_t k[8] = {0};
-        const int bit = W * i;
+        const int extra = (!top && i == G::NW - 1) ? G::EXCESS : 0;
+        const int bit = W * i - extra;
         uint64_t v = (uint64_t)(j + 1) << (bit & 31);
         k[bit >> 5] = (uint32_t)v;
         if ((bit >> 5) + 1 < 8) k[(bit >> 5) + 1] = (uint32_t)(v >> 32);
         LocalTable tbl;
         ext_point acc;
         scalar_mul_core(acc, B, k, tbl);
-        if (top)
-            for (int d = 0; d < W; d++) point_double(acc, acc);
+        for (int d = 0; d < (top ? W : extra); d++) point_double(acc, acc);
         fe zi;
         fe_invert<FqP>(zi, acc.z);
         aff_point a;
@@ -126,18 +126,24 @@ static void fixed_table(const void* base_affine, uint32_t* table, int first, int
         std::memcpy(table + (size_t)e * 24, &nn, 96);
     }
 }
-extern "C" int emul_fixed_table_words(int w) { return (w == 4 ? FixedGeom<4>::ENTRIES : FixedGeom<7>::ENTRIES) * 24; }
+extern "C" int emul_fixed_table_words(int w) {
+    return (w == 4 ? FixedGeom<4>::ENTRIES : w == 7 ? FixedGeom<7>::ENTRIES : w == 16 ? FixedGeom<16>::ENTRIES : FixedGeom<12>::ENTRIES) * 24;
+}
 // builds entries [first, first + count) of the table in place
 extern "C" void emul_fixed_table(const void* base_affine, uint32_t* table, int w, int first, int count) {
     if (w == 4) fixed_table<4>(base_affine, table, first, count);
-    else fixed_table<7>(base_affine, table, first, count);
+    else if (w == 7) fixed_table<7>(base_affine, table, first, count);
+    else if (w == 16) fixed_table<16>(base_affine, table, first, count);
+    else fixed_table<12>(base_affine, table, first, count);
 }
 extern "C" void emul_scalar_mul_fixed(const uint32_t* table, const void* k_, void* out_, size_t n, int w) {
     fixed_table_view v{table};
     for (size_t i = 0; i < n; i++) {
         ext_point acc;
         if (w == 4) scalar_mul_fixed_core<4, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
-        else scalar_mul_fixed_core<7, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
+        else if (w == 7) scalar_mul_fixed_core<7, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
+        else if (w == 16) scalar_mul_fixed_core<16, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
+        else scalar_mul_fixed_core<12, true>(acc, ((const uint32_t*)k_) + 8 * i, v);
         ((ext_point*)out_)[i] = acc;
     }
 }

@@ -321,7 +321,9 @@ def test_mul_consistency_and_assoc(eng, oracle):
     assert oracle.ext_eq(lhs, eng.scalar_mul_vartime(p, scalar_bytes(3938000)))[0]
 
 
-@pytest.mark.parametrize("variant", [0, 100])  # 0: 7-bit windows (216 KB table); 100: 4-bit windows (47 KB)
+# 0: 12-bit windows, 4.1 MB table in global memory (default); 116: 16-bit windows, 50 MB; 107: 7-bit windows, 216 KB in shared
+# memory; 100: 4-bit, 47 KB
+@pytest.mark.parametrize("variant", [0, 116, 107, 100])
 def test_scalar_mul_fixed(eng, oracle, variant):
     eng.set_scalar_mul_variant(variant)
     try:

@@ -222,17 +222,19 @@ def test_emulated_points_and_scalar_mul(emul, oracle):
     assert oracle.ext_eq(got_ct, want).all()
     assert (oracle.batch_normalize(got_ct) == oracle.batch_normalize(want)).all()
     want = oracle.batch_normalize(oracle.scalar_mul_fixed(oracle.generator(), k))
-    for w in (4, 7):  # both window widths of the fixed-base table
+    for w in (4, 7, 12, 16):  # the window widths of the fixed-base tables (4, 7: shared memory; 12, 16: global memory)
         # the table the device kernel builds, computed here by the oracle: entry e = (j+1) * 2^(w*i) * G
         nw, per = -(-252 // w), 1 << (w - 1)
         mult = [(j + 1) << (w * i) for i in range(nw) for j in range(per)] + [1 << (w * nw)]
-        # 2^(w*nw) >= 2^252 is outside multiply()'s 252-bit range: build it as 2^(w*(nw-1)) * G doubled w times
-        sc = scalar_bytes(*[m if m < (1 << 252) else 1 << (w * (nw - 1)) for m in mult])
+        # multiples >= 2^252 are outside multiply()'s 252-bit range (the top-carry entry 2^(w*nw), and for w = 16 the upper
+        # part of the top window): build them as [m >> s] G doubled s times
+        shift = [0 if m < (1 << 252) else m.bit_length() - 252 for m in mult]
+        shift[-1] = w  # the top-carry entry: 2^(w*(nw-1)) G doubled w times
+        sc = scalar_bytes(*[m >> s_ for m, s_ in zip(mult, shift)])
         ext = oracle.scalar_mul_fixed(oracle.generator(), sc)
-        top = ext[-1:]
-        for _ in range(w):
-            top = oracle.ext_double(top)
-        ext[-1] = top[0]
+        for s_ in range(1, max(shift) + 1):
+            idx = np.flatnonzero(np.array(shift) >= s_)
+            ext[idx] = oracle.ext_double(np.ascontiguousarray(ext[idx]))   # one more doubling for everything that owes >= s_
         tbl = oracle.affine_to_niels(oracle.batch_normalize(ext)).view(np.uint32).reshape(-1, 24)
         assert tbl.size == emul.table_words(w)
         for first in (0, per - 1, (nw // 2) * per + 3, nw * per - 2):  # incl. the top-carry entry
