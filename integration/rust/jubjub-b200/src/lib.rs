@@ -266,7 +266,8 @@ impl Engine {
     }
 
     /// `[scalars[i]] base` with one shared base (`&AffinePoint * &Fr`, `AffineNielsPoint::multiply`,
-    /// `src/lib.rs:271-295`): the device keeps a 216 KB window table of the base in shared memory.
+    /// `src/lib.rs:271-295`): the device builds a 12-bit window table of the base (4.1 MB, L2-resident)
+    /// once per base and every scalar is then 22 table additions.
     ///
     /// The base crosses the ABI as Montgomery limbs; out of crate they are obtained without touching private
     /// fields by decoding the base's encoding on the device (`jj_batch_from_bytes` into a device buffer).

@@ -15,6 +15,7 @@ if [ -z "$SKIP_NCU" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench_steps2.csv python bench.py --steps 2 --warmup 3 > /dev/null 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scalar_mul -s 1 -c 1 -o gpurun_out/${tag}_smul_prof python scripts/run_smul.py --logn 20 --reps 3 > /dev/null 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_is_torsion_free -s 1 -c 1 -o gpurun_out/${tag}_torsion_prof python scripts/run_smul.py --logn 20 --reps 3 --what torsion > /dev/null 2>&1; echo "ncu torsion rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scalar_mul_fixed_gmem -s 1 -c 1 -o gpurun_out/${tag}_fixed_prof python scripts/run_smul.py --logn 20 --reps 3 --what fixed > /dev/null 2>&1; echo "ncu fixed rc=$?"
 fi
 cat gpurun_out/${tag}_bench_n1.json | cut -c1-900
 if [ -n "$SANITIZE" ]; then
