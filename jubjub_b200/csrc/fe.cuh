@@ -891,5 +891,46 @@ JJ_DEVICE bool fq_sqrt(fe& r, const fe& a) {
     r = x;
     return true;
 }
+// r = sqrt(num / den) without an inversion (den != 0).  With w = num * den and x = w^((T-1)/2): w x^2 = w^T = b lies in
+// the 2^32-torsion, and g^s = b^(-1/2) as in fq_sqrt, so x g^s = w^(-1/2) and num * w^(-1/2) = sqrt(num / den).  num / den is a
+// residue iff w is (they differ by den^2).  Costs two products more than fq_sqrt and replaces the batched inversion of
+// the denominators in batch_from_bytes (src/lib.rs:596-600): the decoded point is the same, because the root's sign is
+// fixed from the encoding afterwards (src/lib.rs:518-520).
+JJ_DEVICE bool fq_sqrt_ratio(fe& r, const fe& num, const fe& den) {
+#if defined(JJ_HOST_EMUL)
+    if (!g_fq_sqrt_tab.ready) fq_sqrt_tables_build(g_fq_sqrt_tab);
+#endif
+    fe w, x, b, y, f;
+    mont_mul<FqP>(w, num, den);
+    fe_set_zero(r);
+    if (fe_is_zero(w)) return fe_is_zero(num);
+    const FqSqrtTables& t = g_fq_sqrt_tab;
+    fe_pow_const<FqP, ExpFqSqrt>(x, w);  // w^((T-1)/2)
+    mont_mul<FqP>(b, w, x);              // w^((T+1)/2)
+    mont_mul<FqP>(b, b, x);              // w^T
+    uint32_t dlog = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        y = b;
+#pragma unroll 1
+        for (int j = 0; j < 24 - 8 * k; j++) mont_sqr<FqP>(y, y);
+        uint32_t d = t.hash[fq_sqrt_key(y)];
+        dlog |= d << (8 * k);
+        if (k < 3) {
+            fe_load_tab(f, &t.neg[k][d & 255u]);
+            mont_mul<FqP>(b, b, f);
+        }
+    }
+    if (dlog & 1u) return false;
+    uint32_t s = (0x80000000u - (dlog >> 1)) & 0x7fffffffu;
+    mont_mul<FqP>(x, x, num);
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        fe_load_tab(f, &t.pos[k][(s >> (8 * k)) & 255u]);
+        mont_mul<FqP>(x, x, f);
+    }
+    r = x;
+    return true;
+}
 
 }  // namespace jj

@@ -488,10 +488,10 @@ int32_t normalize_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, s
     return JJ_OK;
 }
 int32_t from_bytes_launch(jj_ctx* c, cudaStream_t s, const char* in, char* out, uint8_t* ok, size_t n, bool zip216) {
-    // chains of up to 16 encodings per thread (one wave of 4 x 128-thread blocks per SM covers 1.2 M encodings): the Fermat
-    // inversion is amortised over the chain; grid in whole multiples of the SM count.  8 -> 16 per thread: 5.45 -> 5.26 ms
-    // per 2^20 (the wire path's 8-round chunks keep chains of 8)
-    k_from_bytes<<<chain_grid(c, n, 16, 4), 128, 0, s>>>(in, out, ok, n, zip216);
+    // one thread per encoding (no inversion chain: the root of the quotient comes out of one power, fe.cuh); plain blocks
+    // of 128, so the tail of the batch is balanced by the block scheduler
+    const size_t blocks = std::min<size_t>((n + 127) / 128, (size_t)1 << 24);
+    k_from_bytes<<<(unsigned)std::max<size_t>(1, blocks), 128, 0, s>>>(in, out, ok, n, zip216);
     c->launches++;
     CU(c, cudaGetLastError());
     return JJ_OK;
@@ -549,16 +549,17 @@ int32_t smul_any(jj_ctx* c, cudaStream_t s, Staging* S, const char* pts, bool in
 // whole rounds per staged chunk: a chunk that ends in a partly filled round leaves the multiplier pipe
 // under-occupied for that round.  `rounds` = 1 keeps the exposed first upload / last download small (the 352 B/unit
 // ExtendedPoint path); the wire-format path moves 65 B/unit and wants chunks of several rounds instead, so that the
-// decode kernel's threads amortise their Fermat inversion over a chain of encodings.
+// normalise pass between two scalar-mul launches amortises its Fermat inversion over a chain of points (wire_rounds()).
 size_t smul_chunk(const jj_ctx* c, int rounds = 1) {
     const size_t round = smul_round(c);
     return round ? round * rounds : kChunkUnits;
 }
 
-// Rounds per staged chunk of the wire-format path.  Measured per 2^20 units (pinned host buffers, scripts/wire_sweep.py):
-// 1 round 47.1 ms, 2: 43.5, 4: 41.8, 6: 41.4, 8: 40.8, 14 (one chunk): 41.2 -- against 39.5 ms device-resident.  Eight rounds
-// give the decode kernel chains of 8 encodings per thread (its device-resident efficiency).  A smaller first chunk (to shorten
-// the one upload nothing overlaps) was measured and does not pay: 40.9 (none) / 40.9 (1 round) / 41.1 (2) / 41.4 ms (4).
+// Rounds per staged chunk of the wire-format path.  Measured per 2^20 units (pinned host buffers, scripts/wire_sweep.py)
+// with the inversion-free decode: 1 round 42.0 ms, 2: 40.5, 4: 39.9, 8: 39.3-39.4 -- against 38.0 ms device-resident.  What a
+// small chunk pays is the normalise pass (one Fermat inversion per thread for a chain of two points when the chunk is one
+// round) between two scalar-mul launches that each fill the chip.  Chunks that ramp 1, 2, 4, 4, 2, 1 rounds (small first
+// upload, small last download) were measured and lose for the same reason: 39.8 ms.
 // JJ_WIRE_ROUNDS overrides (experiments).
 int env_rounds(const char* name, int dflt) {
     const char* e = getenv(name);

@@ -809,61 +809,19 @@ __global__ void __launch_bounds__(256) k_affine_to_bytes(const char* __restrict_
     }
 }
 
-// AffinePoint::batch_from_bytes (src/lib.rs:541-627) with the reference's batched inversion (ff::BatchInvert,
-// :596-600): each thread runs Montgomery's trick along its strided chain of encodings (t, t+T, ...), so the
-// denominators 1 + d v^2 cost one Fermat inversion per thread instead of one per encoding.  Scratch is the
-// output itself: out[i].u holds the running prefix product, out[i].v the denominator (0 marks a
-// non-canonical v, which the reference also feeds to the inverter as zero = skipped).  ok[i] = 0 and (0, 0)
-// for rejected encodings.
+// AffinePoint::batch_from_bytes (src/lib.rs:541-627).  The reference batches the inversion of the denominators
+// 1 + d v^2 (ff::BatchInvert, :596-600) because an inversion costs as much as the square root that follows; here the
+// root of the quotient comes out of one power of num * den (fq_sqrt_ratio, fe.cuh), so there is nothing left to batch:
+// one thread per encoding, no scratch, no second pass.  ok[i] = 0 and (0, 0) for rejected encodings.
 __global__ void __launch_bounds__(128, 4) k_from_bytes(const char* __restrict__ in, char* __restrict__ out,
                                                        uint8_t* __restrict__ ok, size_t n, bool zip216) {
-    const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    fe acc, one, d;
-    fe_set_one<FqP>(acc);
-    fe_set_one<FqP>(one);
-    JJ_LOAD_CONST(d, Curve::D);
-    size_t cnt = 0;
-    for (size_t i = t; i < n; i += T, cnt++) {
-        fe vraw, den;
-        ld_fe(vraw, in + i * 32);
-        vraw.w[7] &= 0x7fffffffu;
-        st_fe(out + i * 64, acc);
-        if (fe_is_canonical<FqP>(vraw)) {
-            fe v, v2;
-            fe_from_raw<FqP>(v, vraw);
-            fq_sqr(v2, v);
-            fq_mul(den, d, v2);
-            fe_add<FqP>(den, one, den);  // 1 + d v^2, never zero (-1/d is a non-residue)
-            fq_mul(acc, acc, den);
-        } else {
-            fe_set_zero(den);
-        }
-        st_fe(out + i * 64 + 32, den);
-    }
-    fe_invert<FqP>(acc, acc);
-    for (size_t c = cnt; c-- > 0;) {
-        const size_t i = t + c * T;
-        fe vraw, den, pre;
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += T) {
+        fe enc;
         aff_point p;
-        ld_fe(vraw, in + i * 32);
-        ld_fe(pre, out + i * 64);
-        ld_fe(den, out + i * 64 + 32);
-        const uint32_t sign = vraw.w[7] >> 31;
-        vraw.w[7] &= 0x7fffffffu;
-        fe_set_zero(p.u);
-        fe_set_zero(p.v);
-        bool good = false;
-        if (!fe_is_zero(den)) {
-            fe inv, v, v2, num, u2;
-            fq_mul(inv, pre, acc);   // 1 / den_i
-            fq_mul(acc, acc, den);   // inverse of the prefix before i
-            fe_from_raw<FqP>(v, vraw);
-            fq_sqr(v2, v);
-            fe_sub<FqP>(num, v2, one);  // v^2 - 1
-            fq_mul(u2, num, inv);
-            good = point_decode_tail(p, v, u2, sign, zip216);
-        }
+        ld_fe(enc, in + i * 32);
+        const bool good = point_from_bytes(p, enc, zip216);
         st_fe(out + i * 64, p.u);
         st_fe(out + i * 64 + 32, p.v);
         if (ok) ok[i] = good ? 1 : 0;

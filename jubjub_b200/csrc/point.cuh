@@ -297,27 +297,16 @@ JJ_DEVICE void point_to_niels(ext_niels& n, const ext_point& p) { point_to_niels
 JJ_DEVICE void affine_to_niels(aff_niels& n, const aff_point& p) { affine_to_niels_t<false>(n, p); }
 JJ_DEVICE void point_add(ext_point& r, const ext_point& p, const ext_point& q, bool sub) { point_add_t<false>(r, p, q, sub); }
 
-// Tail of AffinePoint::from_bytes_inner / batch_from_bytes (src/lib.rs:515-533, 603-622): u = sqrt(u2), sign fixed
-// from the parity of the canonical u, ZIP-216 rejection of the non-canonical encodings of (0, +-1).
-JJ_DEVICE bool point_decode_tail(aff_point& p, const fe& v, const fe& u2, uint32_t sign, bool zip216) {
-    fe u, un, uc;
-    fe_set_zero(p.u);
-    fe_set_zero(p.v);
-    if (!fq_sqrt(u, u2)) return false;
-    fe_to_canonical<FqP>(uc, u);
-    bool flip = ((uc.w[0] ^ sign) & 1u) != 0;
-    fe_neg<FqP>(un, u);
-    if (zip216 && fe_is_zero(u) && flip) return false;
-    fe_select(p.u, u, un, flip);
-    p.v = v;
-    return true;
-}
-// AffinePoint::from_bytes_inner (src/lib.rs:492-534) for one encoding held as 8 LE words.
+// AffinePoint::from_bytes_inner / batch_from_bytes (src/lib.rs:492-534, 541-627) for one encoding held as 8 LE words:
+// u^2 = (v^2 - 1) / (1 + d v^2), u = sqrt(u^2) with the sign fixed from the parity of the canonical u, ZIP-216 rejection
+// of the non-canonical encodings of (0, +-1).  The reference inverts the denominator (one batched inversion in
+// batch_from_bytes, :596-600) and then takes the root; here the root of the quotient comes out of ONE power of
+// num * den (fq_sqrt_ratio), so decoding needs no inversion, no scratch and no chain across encodings.
 // Returns false (and leaves the zero point) for non-canonical v, off-curve v, or -- with zip216 --
 // the non-canonical encodings of (0, +-1) whose sign bit is set (ZIP 216, src/lib.rs:527-531).
 JJ_DEVICE bool point_from_bytes(aff_point& p, const fe& enc, bool zip216) {
-    fe vraw = enc, v, v2, num, den, inv, u2, one, d;
-    uint32_t sign = vraw.w[7] >> 31;
+    fe vraw = enc, v, v2, num, den, u, un, uc, one, d;
+    const uint32_t sign = vraw.w[7] >> 31;
     vraw.w[7] &= 0x7fffffffu;
     fe_set_zero(p.u);
     fe_set_zero(p.v);
@@ -329,9 +318,14 @@ JJ_DEVICE bool point_from_bytes(aff_point& p, const fe& enc, bool zip216) {
     fe_sub<FqP>(num, v2, one);          // v^2 - 1
     fq_mul(den, d, v2);
     fe_add<FqP>(den, one, den);         // 1 + d v^2 (never zero: -1/d is a non-residue)
-    fe_invert<FqP>(inv, den);
-    fq_mul(u2, num, inv);
-    return point_decode_tail(p, v, u2, sign, zip216);
+    if (!fq_sqrt_ratio(u, num, den)) return false;
+    fe_to_canonical<FqP>(uc, u);
+    const bool flip = ((uc.w[0] ^ sign) & 1u) != 0;
+    fe_neg<FqP>(un, u);
+    if (zip216 && fe_is_zero(u) && flip) return false;
+    fe_select(p.u, u, un, flip);
+    p.v = v;
+    return true;
 }
 JJ_DEVICE bool point_is_identity(const ext_point& p) {  // u == 0 and v == z  src/lib.rs:691-696
     return fe_is_zero(p.u) && fe_eq(p.v, p.z);

@@ -163,6 +163,14 @@ extern "C" void emul_fq_sqrt(const void* a, void* out, uint8_t* ok, size_t n) {
     }
 }
 
+extern "C" void emul_fq_sqrt_ratio(const void* num, const void* den, void* out, uint8_t* ok, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fe r;
+        ok[i] = fq_sqrt_ratio(r, ((const fe*)num)[i], ((const fe*)den)[i]) ? 1 : 0;
+        ((fe*)out)[i] = r;
+    }
+}
+
 extern "C" void emul_fq_sqrt_ts(const void* a, void* out, uint8_t* ok, size_t n) {  // the loop form, for cross-checks
     for (size_t i = 0; i < n; i++) {
         fe r;

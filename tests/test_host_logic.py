@@ -291,6 +291,20 @@ def test_emulated_sqrt_and_decode(built, oracle):
         assert (ok == wok).all() and 0.3 * len(a) < ok.sum() < len(a)
         assert (oracle.fe_batch(FQ, oracle.OP_SQUARE, out[ok == 1]) == a[ok == 1]).all()
         assert (out[ok == 1] == want[wok == 1]).all()  # the same root as the oracle's Tonelli-Shanks
+    # sqrt(num / den) in one power (the inversion-free decode): residuosity flag and root^2 * den == num, on the same
+    # inputs paired with random denominators, with the torsion ladder also used as denominators, and num = 0
+    den = np.concatenate([oracle.fe_stream(FQ, 78, len(a) - len(tors_m)), tors_m[::-1]])
+    num = oracle.fe_batch(FQ, oracle.OP_MUL, a, den)  # num / den = a
+    num2, den2 = np.concatenate([num, a]), np.concatenate([den, den])  # second half: ratio a / den, residuosity unknown
+    q2, q2ok = oracle.fe_invert(FQ, den2)
+    assert q2ok.all()
+    ratio = oracle.fe_batch(FQ, oracle.OP_MUL, num2, q2)
+    _, rok = oracle.fe_sqrt(FQ, ratio)
+    out, ok = np.zeros_like(num2), np.zeros(len(num2), np.uint8)
+    lib.emul_fq_sqrt_ratio(P(num2), P(den2), P(out), P(ok), C.c_size_t(len(num2)))
+    assert (ok == rok).all() and (ok[:len(a)] == wok).all()
+    assert (oracle.fe_batch(FQ, oracle.OP_SQUARE, out[ok == 1]) == ratio[ok == 1]).all()
+    assert ok[0] == 1 and not out[0].any() and not out[ok == 0].any()
     g = oracle.affine_to_extended(oracle.generator())
     t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, 5, 120))
     enc = oracle.affine_to_bytes(oracle.batch_normalize(oracle.scalar_mul(np.repeat(g, 120, axis=0), t)))
