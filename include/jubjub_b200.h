@@ -189,7 +189,11 @@ int32_t jj_scalar_mul(jj_ctx* ctx, const void* points_ext, const void* scalars32
  * device exactly as jj_batch_from_bytes (ZIP-216 rule unless JJ_PRE_ZIP216), multiplies by scalars32[i] and writes
  * the result in the format of jj_scalar_mul (Extended, JJ_OUT_AFFINE or JJ_OUT_BYTES).  ok[i] = 0 marks a rejected
  * encoding; its output unit is then unspecified.  This is `AffinePoint::from_bytes(..) * scalar` for a whole batch
- * with nothing but public types of the reference crate on the caller's side. */
+ * with nothing but public types of the reference crate on the caller's side.
+ * Host buffers: pass page-locked memory (jj_host_alloc, cudaHostAlloc, cudaHostRegister; 32-byte aligned) and the
+ * decode kernel reads points32 in place, scalars32 is uploaded while the chunk is decoded, and JJ_OUT_BYTES results are
+ * stored in place -- no staging copy in front of the first kernel or behind the last (38.4 instead of 39.3 ms per 2^20).
+ * Pageable buffers are staged; the results are the same. */
 int32_t jj_scalar_mul_encoded(jj_ctx* ctx, const void* points32, const void* scalars32, void* out, uint8_t* ok, size_t n,
                               uint32_t flags);
 

@@ -35,6 +35,8 @@ constexpr int kStages = 2;
 
 struct Staging {
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;   // second copy stream: an input the first kernel of the chunk does not read (BatchOpts::late_in)
+    cudaEvent_t late = nullptr;   // ... has arrived
     char* buf[4] = {nullptr, nullptr, nullptr, nullptr};  // up to 3 inputs + 1 output (+ok)
     size_t cap[4] = {0, 0, 0, 0};
     char* tbl = nullptr;  // scalar-mul window-table scratch (gmem variant)
@@ -319,11 +321,36 @@ struct Out {
     void* p;
     size_t unit;
 };
+// Device alias of a pinned, mapped host range (cudaHostAlloc / cudaHostRegister under unified addressing), or nullptr.
+char* mapped_alias(const void* p, size_t bytes) {
+    if (!p || !bytes || ((uintptr_t)p & 31)) return nullptr;
+    cudaPointerAttributes a0{}, a1{};
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, (const char*)p + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer) return nullptr;
+    return (char*)a0.devicePointer;
+}
+// How a host-pointer call is staged.
+struct BatchOpts {
+    size_t chunk_units = kChunkUnits;  // units per staged chunk (the staging buffers grow to it)
+    bool direct_in0 = false;   // ins[0]: when the caller's buffer is pinned, the kernel reads it in place over PCIe (coalesced
+                               // 32-byte units, a compute-bound consumer) instead of waiting for an upload
+    bool direct_out0 = false;  // outs[0]: ... the producing kernel stores into it in place (write-only 32-byte units)
+    int late_in = -1;          // this input is uploaded on the stage's second stream while the chunk's first kernel runs; the
+                               // launch callback waits for Staging::late before the kernel that reads it
+};
+BatchOpts chunked(size_t units) {
+    BatchOpts o;
+    o.chunk_units = units;
+    return o;
+}
 // Launch(stream, din[3], dout[2], count, staging_or_null) -> status
-// chunk_units: units per staged chunk of a host-pointer call (the staging buffers grow to it).
 template <class Launch>
 int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const Out (&outs)[2], Launch launch,
-                  size_t chunk_units = kChunkUnits) {
+                  const BatchOpts& opts = BatchOpts()) {
+    const size_t chunk_units = opts.chunk_units;
     if (!c) return JJ_ERR_INVALID_ARG;
     for (const In& i : ins)
         if (i.unit && !i.p && n) return fail(c, JJ_ERR_INVALID_ARG, "null input pointer");
@@ -347,6 +374,8 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
         return JJ_OK;
     }
     // host pointers: chunked, double-buffered staging
+    char* const alias_in0 = opts.direct_in0 && ins[0].unit ? mapped_alias(ins[0].p, n * ins[0].unit) : nullptr;
+    char* const alias_out0 = opts.direct_out0 && outs[0].unit && outs[0].p ? mapped_alias(outs[0].p, n * outs[0].unit) : nullptr;
     size_t done = 0;
     int stage = 0;
     while (done < n) {
@@ -359,27 +388,35 @@ int32_t run_batch(jj_ctx* c, uint32_t flags, size_t n, const In (&ins)[3], const
         size_t out_off[2] = {0, 0};
         for (int k = 0; k < 3; k++) {
             if (!ins[k].unit) continue;
+            if (k == 0 && alias_in0) {
+                din[0] = alias_in0 + done * ins[0].unit;
+                continue;
+            }
             int32_t rc = ensure(c, &S.buf[k], &S.cap[k], chunk_units * ins[k].unit, false);
             if (rc) return rc;
+            const bool late = k == opts.late_in;
             CU(c, cudaMemcpyAsync(S.buf[k], (const char*)ins[k].p + done * ins[k].unit, cnt * ins[k].unit,
-                                  cudaMemcpyHostToDevice, S.stream));
+                                  cudaMemcpyHostToDevice, late ? S.aux : S.stream));
+            if (late) CU(c, cudaEventRecord(S.late, S.aux));
             din[k] = S.buf[k];
         }
         {
             size_t need = 0;
             for (int k = 0; k < 2; k++) {
                 out_off[k] = need;
+                if (k == 0 && alias_out0) continue;
                 need += (chunk_units * outs[k].unit + 255) & ~(size_t)255;
             }
-            int32_t rc = ensure(c, &S.buf[3], &S.cap[3], need, false);
+            int32_t rc = ensure(c, &S.buf[3], &S.cap[3], std::max<size_t>(need, 256), false);
             if (rc) return rc;
             for (int k = 0; k < 2; k++)
                 if (outs[k].unit && outs[k].p) dout[k] = S.buf[3] + out_off[k];
+            if (alias_out0) dout[0] = alias_out0 + done * outs[0].unit;
         }
         int32_t rc = launch(S.stream, din, dout, cnt, &S);
         if (rc) return rc;
         for (int k = 0; k < 2; k++)
-            if (outs[k].unit && outs[k].p)
+            if (outs[k].unit && outs[k].p && !(k == 0 && alias_out0))
                 CU(c, cudaMemcpyAsync((char*)outs[k].p + done * outs[k].unit, dout[k], cnt * outs[k].unit,
                                       cudaMemcpyDeviceToHost, S.stream));
         done += cnt;
@@ -570,6 +607,14 @@ int wire_rounds() {
     static const int r = env_rounds("JJ_WIRE_ROUNDS", 8);
     return r;
 }
+// JJ_WIRE_DIRECT=0: stage pinned buffers like pageable ones (A/B)
+bool wire_direct() {
+    static const bool d = [] {
+        const char* e = getenv("JJ_WIRE_DIRECT");
+        return !e || atoi(e) != 0;
+    }();
+    return d;
+}
 
 
 // fixed-base window width: 7 (216 KB table, the default) or 4 (47 KB table, variant 100)
@@ -687,7 +732,10 @@ int32_t jj_init(int device, jj_ctx** out) {
     }
     c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int k = 0; k < kStages && ok; k++) ok = cudaStreamCreateWithFlags(&c->st[k].stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < kStages && ok; k++)
+        ok = cudaStreamCreateWithFlags(&c->st[k].stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&c->st[k].aux, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->st[k].late, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < kStages && ok; k++) ok = cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
@@ -734,6 +782,8 @@ int32_t jj_destroy(jj_ctx* c) {
         if (c->st[k].tbl) cudaFree(c->st[k].tbl);
         if (c->st[k].tmp2) cudaFree(c->st[k].tmp2);
         if (c->st[k].stream) cudaStreamDestroy(c->st[k].stream);
+        if (c->st[k].aux) cudaStreamDestroy(c->st[k].aux);
+        if (c->st[k].late) cudaEventDestroy(c->st[k].late);
     }
     for (void* p : {(void*)c->tbl, (void*)c->tmp, (void*)c->tmp2, (void*)c->norm, (void*)c->fixed_table,
                     (void*)c->fixed_base_dev, (void*)c->flush})
@@ -1102,7 +1152,7 @@ int32_t jj_scalar_mul(jj_ctx* c, const void* points, const void* scalars, void* 
     Out outs[2] = {{out, out_unit(flags)}, {nullptr, 0}};
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
         return smul_any(c, s, S, din[0], false, din[1], dout[0], cnt, flags);
-    }, smul_chunk(c));
+    }, chunked(smul_chunk(c)));
 }
 
 int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scalars, void* out, uint8_t* ok, size_t n,
@@ -1113,6 +1163,14 @@ int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scala
     In ins[3] = {{points32, 32}, {scalars, 32}, {nullptr, 0}};
     Out outs[2] = {{out, out_unit(flags)}, {ok, 1}};
     const bool zip216 = !(flags & JJ_PRE_ZIP216), subgroup = flags & JJ_CHECK_SUBGROUP;
+    // Host buffers: when they are pinned, the decode kernel reads the encodings in place and the normalise + encode pass
+    // stores the 32-byte results in place (both coalesced, both compute-bound kernels), and the scalars -- which only the
+    // scalar-mul kernel reads -- are uploaded while the chunk is being decoded: no upload in front of the first kernel, no
+    // download behind the last one.  Pageable buffers are staged as everywhere else.
+    BatchOpts opts = chunked(smul_chunk(c, wire_rounds()));
+    opts.direct_in0 = wire_direct();
+    opts.direct_out0 = wire_direct() && out_unit(flags) == 32;
+    opts.late_in = wire_direct() ? 1 : -1;
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) -> int32_t {
         // decode -> AffinePoint scratch (64 B) [-> subgroup test on it] -> scalar-mul reading the affine points directly
         char** aff = S ? &S->tmp2 : &c->tmp2;
@@ -1126,8 +1184,9 @@ int32_t jj_scalar_mul_encoded(jj_ctx* c, const void* points32, const void* scala
             c->launches++;
             CU(c, cudaGetLastError());
         }
+        if (S && opts.late_in == 1) CU(c, cudaStreamWaitEvent(s, S->late, 0));  // the scalars have arrived
         return smul_any(c, s, S, *aff, true, din[1], dout[0], cnt, flags);
-    }, smul_chunk(c, wire_rounds()));
+    }, opts);
 }
 
 int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scalars, void* out, size_t n, uint32_t flags) {

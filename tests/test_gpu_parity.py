@@ -555,6 +555,50 @@ def test_scalar_mul_encoded(eng, oracle):
     assert (gd.download()[wok[:70000] == 1] == want[:70000][wok[:70000] == 1]).all()
 
 
+def test_scalar_mul_encoded_pinned_buffers(eng, oracle):
+    """Pinned host buffers: the decode kernel reads the encodings in place, the scalars are uploaded behind the decode,
+    and 32-byte results are stored in place (no staging copies) -- same bytes and flags as the staged path with
+    pageable buffers, for every output format, with the subgroup check, across several chunks, and for a pinned
+    buffer that is not 32-byte aligned (falls back to staging)."""
+    import jubjub_b200 as jj
+    from bench import pinned
+
+    n = 1300000  # three chunks of eight rounds
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 31, n))
+    t[::3, 0] &= 0xF8
+    k = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 32, n))
+    enc = eng.affine_to_bytes(eng.batch_normalize(eng.scalar_mul_fixed_vartime(oracle.generator(), t))).copy()
+    enc[7::53, 0] ^= 1
+    enc[3::211] = 0xFF
+    henc, p1 = pinned(eng, (n + 1, 32), np.uint8)
+    hk, p2 = pinned(eng, (n, 32), np.uint8)
+    hok, p3 = pinned(eng, (n,), np.uint8)
+    hout, p4 = pinned(eng, (n, 160), np.uint8)
+    try:
+        henc[:n], hk[:] = enc, k
+        for flags, unit in ((jj.JJ_OUT_BYTES, 32), (jj.JJ_OUT_BYTES | jj.JJ_CHECK_SUBGROUP, 32), (jj.JJ_OUT_AFFINE, 64), (0, 160)):
+            m = n if unit == 32 else 200000
+            want, wok = eng.scalar_mul_encoded_vartime(enc[:m], k[:m], output={32: "bytes", 64: "affine", 160: "extended"}[unit],
+                                                       check_subgroup=bool(flags & jj.JJ_CHECK_SUBGROUP))
+            hout[:] = 0xA5
+            hok[:] = 7
+            eng._check(eng.lib.jj_scalar_mul_encoded(eng.ctx, henc.ctypes.data, hk.ctypes.data, hout.ctypes.data, hok.ctypes.data, m, flags))
+            got = hout.reshape(-1)[: m * unit].reshape(m, unit)
+            assert (hok[:m] == wok).all() and 0 < wok.sum() < m
+            assert (got[wok == 1] == want.view(np.uint8).reshape(m, unit)[wok == 1]).all()
+            assert (hok[m:] == 7).all() and (hout.reshape(-1)[m * unit:] == 0xA5).all()  # nothing written past the batch
+        # pinned but misaligned input (16 bytes in): staged like a pageable buffer, same results
+        m = 100000
+        mis = henc.reshape(-1)[16: 16 + m * 32].reshape(m, 32)
+        mis[:] = enc[:m]
+        want, wok = eng.scalar_mul_encoded_vartime(enc[:m], k[:m])
+        eng._check(eng.lib.jj_scalar_mul_encoded(eng.ctx, mis.ctypes.data, hk.ctypes.data, hout.ctypes.data, hok.ctypes.data, m, jj.JJ_OUT_BYTES))
+        assert (hok[:m] == wok).all() and (hout.reshape(-1)[: m * 32].reshape(m, 32)[wok == 1] == want[wok == 1]).all()
+    finally:
+        for p in (p1, p2, p3, p4):
+            eng.lib.jj_host_free(eng.ctx, p)
+
+
 def test_scalar_mul_encoded_subgroup_check(eng, oracle):
     """JJ_CHECK_SUBGROUP: the decode is SubgroupPoint::from_bytes (src/lib.rs:1427-1429) -- ok[i] = decoded AND
     torsion free -- and accepted units are multiplied as before.  Host (staged chunks) and device resident."""
