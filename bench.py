@@ -49,8 +49,8 @@ BYTES_PER_UNIT = 352
 IMADS_PER_UNIT = 249 * (4 * 84 + 3 * 112) + (7 + 1 + 62 * 15 / 16) * 8 * 112 + 16 * 112
 # from the committed ncu capture of the dominant kernel at 2^20 units (ncu --set full, one launch):
 # dram__bytes_read.sum + dram__bytes_write.sum, and IMAD.WIDE thread instructions executed per unit (source page)
-NCU_PROFILE = "profiles/r02o_ncu_scalar_mul_default_n1048576.csv"
-NCU_DRAM_BYTES_PER_LAUNCH = 226.49e6 + 653.64e6
+NCU_PROFILE = "profiles/r02u_ncu_scalar_mul_default_n1048576.csv"
+NCU_DRAM_BYTES_PER_LAUNCH = 226.21e6 + 657.02e6
 NCU_IMADS_ISSUED_PER_UNIT = 243955
 GEN_RAW = np.array([[0xE4B3D35DF1A7ADFE, 0xCAF55D1B29BF81AF, 0x8B0F03DDD60A8187, 0x62EDCBB8BF3787C8, 0xB, 0, 0, 0]],
                    dtype=np.uint64)
@@ -481,8 +481,9 @@ def main():
                 "ms_per_step": wire_s * 1e3, "device_resident_ms": wire_dev_ms,
                 "device_resident_with_subgroup_check_ms": wire_sub_ms, "matches_headline_results": wire_ok,
                 "note": "jj_scalar_mul_encoded, JJ_OUT_BYTES: AffinePoint::to_bytes encodings + canonical scalars in pinned "
-                        "HOST memory -> batch_from_bytes, scalar-mul, batch_normalize + to_bytes on the device -> encodings "
-                        "+ ok[] back in HOST memory; what integration/rust binds (N = 1, rank 0)"}
+                        "HOST memory -> batch_from_bytes (reads the pinned encodings in place over PCIe; the scalars are "
+                        "uploaded behind it), scalar-mul, batch_normalize + to_bytes on the device (stores the encodings in "
+                        "place) -> encodings + ok[] in HOST memory; what integration/rust binds (N = 1, rank 0)"}
     parity["wire_path_matches"] = wire_ok
     parity["ok"] = bool(parity["ok"] and wire_ok)
 
