@@ -207,6 +207,12 @@ int32_t jj_scalar_mul_fixed(jj_ctx* ctx, const void* base_affine, const void* sc
  * association order is a tree, not the reference's left fold: the result is the same point in other projective
  * coordinates -- JJ_OUT_AFFINE / JJ_OUT_BYTES outputs are bit-exact.  Host or device pointers; not capturable. */
 int32_t jj_point_sum(jj_ctx* ctx, const void* points_ext, void* out, size_t groups, size_t group_size, uint32_t flags);
+/* Neg for ExtendedPoint src/lib.rs:195-210: (-U, V, Z, -T1, T2), all 160 B bit-exact */
+int32_t jj_point_neg(jj_ctx* ctx, const void* p_ext, void* out_ext, size_t n, uint32_t flags);
+/* ConstantTimeEq / PartialEq for ExtendedPoint src/lib.rs:153-163, 177-181: flags_out[i] = (u z' == u' z) & (v z' == v' z) */
+int32_t jj_point_eq(jj_ctx* ctx, const void* p_ext, const void* q_ext, uint8_t* flags_out, size_t n, uint32_t flags);
+/* From<AffinePoint> for ExtendedPoint src/lib.rs:214-226: (u, v) -> (u, v, 1, u, v) */
+int32_t jj_affine_to_extended(jj_ctx* ctx, const void* p_affine, void* out_ext, size_t n, uint32_t flags);
 /* ExtendedPoint::mul_by_cofactor src/lib.rs:722-724 (= double().double().double(), all 160 B bit-exact) */
 int32_t jj_mul_by_cofactor(jj_ctx* ctx, const void* p_ext, void* out_ext, size_t n, uint32_t flags);
 /* ExtendedPoint::batch_normalize src/lib.rs:840-858: ExtendedPoint -> AffinePoint (z = 0 gives (0, 0)

@@ -155,6 +155,23 @@ class Engine {
         check(jj_is_prime_order(ctx_, p.data(), out.data(), p.size(), 0));
         return out;
     }
+    // Neg / PartialEq for ExtendedPoint (src/lib.rs:195-210, 153-181), From<AffinePoint> (:214-226), element by element
+    std::vector<ExtendedPoint> batch_neg(const std::vector<ExtendedPoint>& p) {
+        std::vector<ExtendedPoint> out(p.size());
+        check(jj_point_neg(ctx_, p.data(), out.data(), p.size(), 0));
+        return out;
+    }
+    std::vector<uint8_t> batch_eq(const std::vector<ExtendedPoint>& p, const std::vector<ExtendedPoint>& q) {
+        same(p.size(), q.size());
+        std::vector<uint8_t> out(p.size());
+        check(jj_point_eq(ctx_, p.data(), q.data(), out.data(), p.size(), 0));
+        return out;
+    }
+    std::vector<ExtendedPoint> batch_from_affine(const std::vector<AffinePoint>& a) {
+        std::vector<ExtendedPoint> out(a.size());
+        check(jj_affine_to_extended(ctx_, a.data(), out.data(), a.size(), 0));
+        return out;
+    }
     std::vector<ExtendedPoint> batch_mul_by_cofactor(const std::vector<ExtendedPoint>& p) {
         std::vector<ExtendedPoint> out(p.size());
         check(jj_mul_by_cofactor(ctx_, p.data(), out.data(), p.size(), 0));

@@ -120,6 +120,9 @@ extern "C" {
     pub fn jj_scalar_mul_fixed(ctx: *mut JjCtx, base_affine: *const c_void, scalars32: *const c_void, out: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_point_sum(ctx: *mut JjCtx, points_ext: *const c_void, out: *mut c_void, groups: usize, group_size: usize, flags: u32) -> i32;
     pub fn jj_mul_by_cofactor(ctx: *mut JjCtx, p_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
+    pub fn jj_point_neg(ctx: *mut JjCtx, p_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
+    pub fn jj_point_eq(ctx: *mut JjCtx, p_ext: *const c_void, q_ext: *const c_void, flags_out: *mut u8, n: usize, flags: u32) -> i32;
+    pub fn jj_affine_to_extended(ctx: *mut JjCtx, p_affine: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_batch_normalize(ctx: *mut JjCtx, in_ext: *const c_void, out_affine: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_batch_normalize_extended(ctx: *mut JjCtx, in_ext: *const c_void, out_ext: *mut c_void, n: usize, flags: u32) -> i32;
     pub fn jj_affine_to_bytes(ctx: *mut JjCtx, in_affine: *const c_void, out32: *mut c_void, n: usize, flags: u32) -> i32;

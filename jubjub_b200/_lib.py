@@ -59,6 +59,7 @@ PROTOTYPES = {
     "jj_scalar_mul_encoded": [_vp, _vp, _vp, _vp, _sz, _u32],
     "jj_batch_normalize": _UNARY, "jj_batch_normalize_extended": _UNARY, "jj_affine_to_bytes": _UNARY,
     "jj_mul_by_cofactor": _UNARY, "jj_is_prime_order": _UNARY,
+    "jj_point_neg": _UNARY, "jj_point_eq": _BINARY, "jj_affine_to_extended": _UNARY,
     "jj_point_sum": [_vp, _vp, _sz, _sz, _u32], "jj_point_sum_sharded": [_vp, _vp, _sz, _u32],
     "jj_batch_from_bytes": _WITH_OK,
     "jj_is_torsion_free": _UNARY, "jj_is_identity": _UNARY, "jj_is_small_order": _UNARY,

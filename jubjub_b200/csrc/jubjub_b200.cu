@@ -1066,6 +1066,43 @@ int32_t jj_affine_to_niels(jj_ctx* c, const void* p, void* out, size_t n, uint32
     return pt_binary<PT_AFFINE_TO_NIELS>(c, p, 64, nullptr, 0, out, 96, n, flags);
 }
 
+int32_t jj_point_neg(jj_ctx* c, const void* p, void* out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    In ins[3] = {{p, 160}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{out, 160}, {nullptr, 0}};
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
+        k_point_neg<<<grid_for(c, cnt, 256, 8), 256, 0, s>>>(din[0], dout[0], cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
+    });
+}
+int32_t jj_point_eq(jj_ctx* c, const void* p, const void* q, uint8_t* flags_out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    In ins[3] = {{p, 160}, {q, 160}, {nullptr, 0}};
+    Out outs[2] = {{flags_out, 1}, {nullptr, 0}};
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
+        k_point_eq<<<grid_for(c, cnt, 128, 8), 128, 0, s>>>(din[0], din[1], (uint8_t*)dout[0], cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
+    });
+}
+int32_t jj_affine_to_extended(jj_ctx* c, const void* p, void* out, size_t n, uint32_t flags) {
+    if (!c) return JJ_ERR_INVALID_ARG;
+    if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");
+    In ins[3] = {{p, 64}, {nullptr, 0}, {nullptr, 0}};
+    Out outs[2] = {{out, 160}, {nullptr, 0}};
+    return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging*) -> int32_t {
+        k_affine_to_extended<<<grid_for(c, cnt, 256, 8), 256, 0, s>>>(din[0], dout[0], cnt);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return JJ_OK;
+    });
+}
+
 int32_t jj_mul_by_cofactor(jj_ctx* c, const void* p, void* out, size_t n, uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;
     if (flags & JJ_CANON) return fail(c, JJ_ERR_INVALID_ARG, "point entry points take Montgomery-form coordinates");

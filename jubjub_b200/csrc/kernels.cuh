@@ -287,6 +287,50 @@ __global__ void __launch_bounds__(128) k_point_flag(const char* __restrict__ p, 
         }
     }
 }
+// Neg for ExtendedPoint (src/lib.rs:195-210): (-U, V, Z, -T1, T2), all 160 bytes as the reference's.
+__global__ void __launch_bounds__(256) k_point_neg(const char* __restrict__ p, char* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ext_point P;
+        ld_ext(P, p, i);
+        fe_neg<FqP>(P.u, P.u);
+        fe_neg<FqP>(P.t1, P.t1);
+        st_ext(out, i, P);
+    }
+}
+// ConstantTimeEq for ExtendedPoint (src/lib.rs:153-163): u z' == u' z and v z' == v' z.
+__global__ void __launch_bounds__(128) k_point_eq(const char* __restrict__ p, const char* __restrict__ q, uint8_t* __restrict__ out,
+                                                  size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fe pu, pv, pz, qu, qv, qz, a, b;
+        ld_fe(pu, p + i * 160);
+        ld_fe(pv, p + i * 160 + 32);
+        ld_fe(pz, p + i * 160 + 64);
+        ld_fe(qu, q + i * 160);
+        ld_fe(qv, q + i * 160 + 32);
+        ld_fe(qz, q + i * 160 + 64);
+        fq_mul(a, pu, qz);
+        fq_mul(b, qu, pz);
+        bool eq = fe_eq(a, b);
+        fq_mul(a, pv, qz);
+        fq_mul(b, qv, pz);
+        out[i] = (eq && fe_eq(a, b)) ? 1 : 0;
+    }
+}
+// From<AffinePoint> for ExtendedPoint (src/lib.rs:214-226): (u, v) -> (u, v, 1, u, v).
+__global__ void __launch_bounds__(256) k_affine_to_extended(const char* __restrict__ p, char* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ext_point P;
+        ld_fe(P.u, p + i * 64);
+        ld_fe(P.v, p + i * 64 + 32);
+        fe_set_one<FqP>(P.z);
+        P.t1 = P.u;
+        P.t2 = P.v;
+        st_ext(out, i, P);
+    }
+}
 // mul_by_cofactor (src/lib.rs:722-724): three doublings with the reference's formula sequence => all 160 bytes equal.
 __global__ void __launch_bounds__(128) k_mul_by_cofactor(const char* __restrict__ p, char* __restrict__ out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;

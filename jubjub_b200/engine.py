@@ -280,6 +280,19 @@ class Engine:
         """ExtendedPoint::mul_by_cofactor (src/lib.rs:722-724)."""
         return self._call("jj_mul_by_cofactor", [(p, EXT_W, np.uint64)], EXT_W, out=out)
 
+    def point_neg(self, p, out=None):
+        """Neg for ExtendedPoint (src/lib.rs:195-210): (-U, V, Z, -T1, T2)."""
+        return self._call("jj_point_neg", [(p, EXT_W, np.uint64)], EXT_W, out=out)
+
+    def point_eq(self, p, q):
+        """ConstantTimeEq for ExtendedPoint (src/lib.rs:153-163), element by element: flags[i] = (p[i] == q[i])."""
+        o = self._call("jj_point_eq", [(p, EXT_W, np.uint64), (q, EXT_W, np.uint64)], 1, np.uint8)
+        return o if isinstance(o, DeviceArray) else o.reshape(-1)
+
+    def affine_to_extended(self, a, out=None):
+        """From<AffinePoint> for ExtendedPoint (src/lib.rs:214-226): (u, v) -> (u, v, 1, u, v)."""
+        return self._call("jj_affine_to_extended", [(a, AFF_W, np.uint64)], EXT_W, out=out)
+
     def affine_to_bytes(self, a, out=None):
         return self._call("jj_affine_to_bytes", [(a, AFF_W, np.uint64)], 32, np.uint8, out=out)
 

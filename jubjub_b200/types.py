@@ -321,8 +321,7 @@ class ExtendedPoint:
 
     @classmethod
     def from_affine(cls, a):
-        one = Fq.one(len(a), a.eng).limbs
-        return cls(np.concatenate([a.data, one, a.data], axis=1), a.eng)  # (u, v, 1, u, v), src/lib.rs:214-226
+        return cls(a.eng.affine_to_extended(a.data), a.eng)  # (u, v, 1, u, v), src/lib.rs:214-226
 
     @classmethod
     def identity(cls, n=1, engine=None):
@@ -357,10 +356,7 @@ class ExtendedPoint:
         return self._addsub(o, True)
 
     def __neg__(self):  # (-U, V, Z, -T1, T2), src/lib.rs:196-210
-        d = self.data.copy()
-        d[:, 0:4] = self.eng.fe_neg("fq", self.data[:, 0:4])
-        d[:, 12:16] = self.eng.fe_neg("fq", self.data[:, 12:16])
-        return ExtendedPoint(d, self.eng)
+        return ExtendedPoint(self.eng.point_neg(self.data), self.eng)
 
     def mul_vartime(self, k):
         """`&ExtendedPoint * &Fr` (src/lib.rs:873-879), variable-time in the scalar."""
@@ -409,10 +405,11 @@ class ExtendedPoint:
         """(u/z, v/z) == (u'/z', v'/z') via u*z' == u'*z and v*z' == v'*z (src/lib.rs:153-163)."""
         if not isinstance(o, ExtendedPoint) or len(o) != len(self):
             return False
-        m = lambda a, b: self.eng.fe_mul("fq", np.ascontiguousarray(a), np.ascontiguousarray(b))  # noqa: E731
-        s, t = self.data, o.data
-        return bool((m(s[:, 0:4], t[:, 8:12]) == m(t[:, 0:4], s[:, 8:12])).all()
-                    and (m(s[:, 4:8], t[:, 8:12]) == m(t[:, 4:8], s[:, 8:12])).all())
+        return bool(self.eq(o).all())
+
+    def eq(self, o):
+        """Element by element: flags[i] = (self[i] == o[i]) as points (src/lib.rs:153-163)."""
+        return self.eng.point_eq(self.data, o.data).astype(bool)
 
     __hash__ = None
 

@@ -30,6 +30,7 @@ pts, ok = eng.batch_from_bytes(out)
 assert ok.all()
 eng.is_torsion_free(p); eng.is_torsion_free(p[:64], ladder=True); eng.is_prime_order(p); eng.is_identity(p); eng.is_small_order(p)
 eng.mul_by_cofactor(p); eng.batch_normalize_extended(q)
+assert eng.point_eq(p, eng.point_neg(eng.point_neg(p))).all(); eng.affine_to_extended(eng.batch_normalize(q))
 enc, ok2 = eng.scalar_mul_encoded_vartime(out, k, check_subgroup=True)
 d = eng.to_device(p); eng.scalar_mul_vartime(d, eng.to_device(k), output="affine").download()
 # chains longer than one element per thread (Montgomery-trick kernels) at a size compute-sanitizer finishes quickly:

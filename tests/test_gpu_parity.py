@@ -390,6 +390,46 @@ def test_batch_normalize_and_flags(eng, oracle):
     assert (eng.mul_by_cofactor(q) == oracle.ext_mul_by_cofactor(q)).all()
 
 
+def test_point_neg_eq_from_affine(eng, oracle):
+    """Neg / PartialEq for ExtendedPoint and From<AffinePoint> (src/lib.rs:153-226) as batch kernels: negation and the
+    affine -> extended map bit-exact on all 160 bytes against the oracle's field ops, equality against the oracle's
+    normalised points -- equal points in different projective scalings, P vs -P, P vs P + T for the 8-torsion, and the
+    points of order two and one, whose negation equals themselves."""
+    n = 3000
+    g = oracle.affine_to_extended(oracle.generator())
+    t = oracle.fe_to_bytes(FR, oracle.fe_stream(FR, M.SEED0 + 41, n))
+    p = oracle.scalar_mul(np.repeat(g, n, axis=0), t)  # z != 1
+    tors = oracle.affine_to_extended(affine_raw(oracle, K.EIGHT_TORSION_RAW))
+    p[:8] = tors
+    # negation: (-U, V, Z, -T1, T2)
+    want = p.copy()
+    want[:, 0:4] = oracle.fe_batch(FQ, oracle.OP_NEG, np.ascontiguousarray(p[:, 0:4]))
+    want[:, 12:16] = oracle.fe_batch(FQ, oracle.OP_NEG, np.ascontiguousarray(p[:, 12:16]))
+    neg = eng.point_neg(p)
+    assert (neg == want).all()
+    assert (eng.point_neg(eng.to_device(p)).download() == want).all()
+    # from affine
+    aff = oracle.batch_normalize(p)
+    assert (eng.affine_to_extended(aff) == oracle.affine_to_extended(aff)).all()
+    # equality: q = p rescaled by a random lambda (same point), r = p + T_j (different unless T_j = O), -p
+    lam = oracle.fe_stream(FQ, M.SEED0 + 42, n)
+    q = p.copy()
+    for c in range(3):
+        q[:, 4 * c:4 * c + 4] = oracle.fe_batch(FQ, oracle.OP_MUL, np.ascontiguousarray(p[:, 4 * c:4 * c + 4]), lam)
+    assert eng.point_eq(p, q).all() and eng.point_eq(q, p).all()
+    r = eng.point_add(p, np.tile(tors, (n // 8, 1)))
+    ar = oracle.batch_normalize(r)
+    want_eq = (ar == aff).all(axis=1)
+    got = eng.point_eq(p, r)
+    assert (got == want_eq).all() and 0.1 * n < got.sum() < 0.15 * n  # T_j = O for one j in eight
+    an = oracle.batch_normalize(neg)
+    self_neg = (an == aff).all(axis=1)
+    assert (eng.point_eq(p, neg) == self_neg).all() and 0 < self_neg.sum() <= 2  # only the identity and (0, -1)
+    assert (eng.point_eq(eng.to_device(p), eng.to_device(r)).download().ravel() == want_eq).all()
+    with pytest.raises(Exception):
+        eng.point_eq(p, q[:-1])
+
+
 def _oracle_sum(oracle, p):
     """Sum of the rows of p by halving with the oracle's `&ExtendedPoint + &ExtendedPoint` (any order gives the same point)."""
     p = p.copy()
