@@ -32,6 +32,13 @@ eng.is_torsion_free(p); eng.is_torsion_free(p[:64], ladder=True); eng.is_prime_o
 eng.mul_by_cofactor(p); eng.batch_normalize_extended(q)
 assert eng.point_eq(p, eng.point_neg(eng.point_neg(p))).all(); eng.affine_to_extended(eng.batch_normalize(q))
 enc, ok2 = eng.scalar_mul_encoded_vartime(out, k, check_subgroup=True)
+# the same through page-locked buffers: encodings read in place, scalars uploaded behind the decode, results stored in place
+from bench import pinned  # noqa: E402
+hp = [pinned(eng, (len(k), 32), np.uint8) for _ in range(3)] + [pinned(eng, (len(k),), np.uint8)]
+hp[0][0][:], hp[1][0][:] = out, k
+eng._check(eng.lib.jj_scalar_mul_encoded(eng.ctx, hp[0][0].ctypes.data, hp[1][0].ctypes.data, hp[2][0].ctypes.data,
+                                         hp[3][0].ctypes.data, len(k), jj.JJ_OUT_BYTES | jj.JJ_CHECK_SUBGROUP))
+assert (hp[3][0] == ok2).all() and (hp[2][0][ok2 == 1] == enc[ok2 == 1]).all()
 d = eng.to_device(p); eng.scalar_mul_vartime(d, eng.to_device(k), output="affine").download()
 # chains longer than one element per thread (Montgomery-trick kernels) at a size compute-sanitizer finishes quickly:
 # the grids are capped at one 128-thread block per 128 elements, so force chains by calling with few elements is not

@@ -63,6 +63,16 @@ int main(int argc, char** argv) {
             auto again = eng.batch_normalize(eng.batch_sum(halves));
             if (std::memcmp(whole.data(), again.data(), sizeof(AffinePoint)) != 0) return 13;
         }
+        // Neg / PartialEq / From<AffinePoint> (src/lib.rs:153-226): p == from_affine(normalize(p)), -(-p) == p bit for bit,
+        // p + (-p) == identity == its own negation
+        auto back = eng.batch_from_affine(a0);
+        auto eq1 = eng.batch_eq(p, back);
+        auto nn = eng.batch_neg(eng.batch_neg(p));
+        if (std::memcmp(nn.data(), p.data(), n * sizeof(ExtendedPoint)) != 0) return 14;
+        auto zero = eng.batch_add(p, eng.batch_neg(p));
+        auto eq2 = eng.batch_eq(zero, eng.batch_neg(zero)), eq3 = eng.batch_eq(p, eng.batch_double(p));
+        for (uint64_t i = 0; i < n; i++)
+            if (!eq1[i] || !eq2[i] || eq3[i]) return 15;
         bool threw = false;
         try {
             k.pop_back();
