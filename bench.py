@@ -220,6 +220,44 @@ def run_reference(args, rank, emit=print):
     }))
 
 
+_FULL_AFFINITY = set()
+
+
+def bind_host_to_gpu(local):
+    """N > 1: run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, so that the pinned buffers it
+    allocates next (first touch) are local to that GPU's PCIe root -- without it the ranks of the far socket stage every
+    chunk across the inter-socket link.  Best effort: returns what was done for the JSON line.  JJ_NUMA_BIND=0 disables."""
+    info = {"bound": False}
+    if os.environ.get("JJ_NUMA_BIND", "1") == "0":
+        info["why"] = "JJ_NUMA_BIND=0"
+        return info
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info.update({"gpu": bdf, "numa_node": node, "local_cpus": len(cpus), "allowed_cpus": len(allowed), "usable": len(use)})
+        if node < 0 or not use:
+            info["why"] = "no NUMA information" if node < 0 else "none of the GPU's local CPUs is in this process's cpuset"
+            return info
+        if use != allowed:
+            _FULL_AFFINITY.update(allowed)  # given back before the CPU-baseline leg
+            os.sched_setaffinity(0, use)
+        info["bound"] = True
+    except Exception as e:  # noqa: BLE001 -- best effort, never fatal
+        info["why"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def workload_log2(args):
     if args.units_log2:
         return args.units_log2
@@ -277,11 +315,13 @@ def main():
     import jubjub_b200 as jj
 
     dist = None
+    numa = {"bound": False, "why": "single GPU"}
     if world > 1:
         import torch
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
+        numa = bind_host_to_gpu(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = jj.Engine(local)
     logn = workload_log2(args)
@@ -385,6 +425,10 @@ def main():
     parity["e2e_host_copy_matches_gather"] = e2e_same
     parity["ok"] = bool(parity["ok"] and e2e_same)
 
+    numa_all = [numa]
+    if dist is not None:
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -488,6 +532,8 @@ def main():
     parity["ok"] = bool(parity["ok"] and wire_ok)
 
     # ---- CPU baseline: the oracle (reference algorithm, C) on this box's host cores, bounded sample
+    if _FULL_AFFINITY:
+        os.sched_setaffinity(0, _FULL_AFFINITY)  # all host cores again (N > 1 bound this rank to its GPU's NUMA node)
     sample = min(n, int(os.environ.get("JJ_CPU_SAMPLE", str(12288 * cores))))
     sp, sk = hp[:sample].copy(), hk[:sample].copy()
     from oracle import binding as ob
@@ -507,6 +553,7 @@ def main():
         "config": {"workload": workload_name(world, logn), "units_per_gpu": n, "total_units": world * n,
                    "output": "ExtendedPoint (160 B)" if out_fmt == "extended" else "32-byte encodings (normalise + encode fused into the kernel)",
                    "collective": collective,
+                   **({"host_numa_binding": numa_all} if world > 1 else {}),
                    "cache": f"inputs+outputs {352 * n / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed); kernel is integer-bound"},
         "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * n * 192,
                 "d2h_bytes_per_step": world * n * unit_out, "ms_per_step": e2e_s * 1e3,
