@@ -81,6 +81,21 @@ class Engine:
     def empty(self, shape, dtype=np.uint64):
         return DeviceArray(self, shape, dtype)
 
+    def pinned_empty(self, shape, dtype=np.uint64):
+        """A numpy array in page-locked host memory (jj_host_alloc), freed when the array is garbage-collected.  Host
+        batches passed in such arrays are copied by DMA without the driver's pageable staging, and the wire-format
+        path (scalar_mul_encoded_vartime with out= / ok=... through the C ABI) reads and writes them in place."""
+        import weakref
+
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.jj_host_alloc(self.ctx, nbytes, C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        lib, ctx, addr = self.lib, self.ctx, p.value
+        weakref.finalize(buf, lambda: lib.jj_host_free(ctx, C.c_void_p(addr)) if ctx else None)
+        return arr
+
     def to_device(self, host):
         host = np.ascontiguousarray(host)
         return DeviceArray(self, host.shape, host.dtype).upload(host)
@@ -111,7 +126,7 @@ class Engine:
     def _ptr(x):
         return x.ptr if isinstance(x, DeviceArray) else x.ctypes.data
 
-    def _call(self, name, ins, out_width, out_dtype=np.uint64, flags=0, out=None, ok=False, extra_pre=()):
+    def _call(self, name, ins, out_width, out_dtype=np.uint64, flags=0, out=None, ok=False, extra_pre=(), ok_out=None):
         """ins: list of (array, width, dtype).  Returns out (and ok flags when ok=True)."""
         args, n, dev, keep = [], None, None, []
         for a, w, dt in ins:
@@ -129,7 +144,7 @@ class Engine:
         call = list(extra_pre) + args + [self._ptr(o)]
         okbuf = None
         if ok:
-            okbuf = self._out(dev, n, 1, np.uint8)
+            okbuf = self._out(dev, n, 1, np.uint8, ok_out if ok_out is None or isinstance(ok_out, DeviceArray) else ok_out.reshape(-1, 1))
             call.append(self._ptr(okbuf))
         f = flags | (L.JJ_DEVICE_PTRS if dev else 0)
         self._check(getattr(self.lib, name)(self.ctx, *call, n, f))
@@ -224,15 +239,17 @@ class Engine:
         return self._call("jj_scalar_mul", [(points, EXT_W, np.uint64), sc], w, dt,
                           flags=f | flags | (L.JJ_SCALAR_MONT if scalar_mont else 0), out=out)
 
-    def scalar_mul_encoded_vartime(self, encodings, scalars, output="bytes", zip216=True, check_subgroup=False, flags=0):
+    def scalar_mul_encoded_vartime(self, encodings, scalars, output="bytes", zip216=True, check_subgroup=False, flags=0,
+                                   out=None, ok_out=None):
         """(out, ok): out[i] = [scalars[i]] AffinePoint::from_bytes(encodings[i]) -- wire format in (32-byte
         encodings, src/lib.rs:455-464), decoded on the device (src/lib.rs:541-627); ok[i] = 0 for a rejected
         encoding (its output unit is unspecified).  check_subgroup: the decode is SubgroupPoint::from_bytes
-        (src/lib.rs:1427-1429), i.e. ok[i] also requires is_torsion_free.  Variable-time."""
+        (src/lib.rs:1427-1429), i.e. ok[i] also requires is_torsion_free.  Variable-time.  With host arrays from
+        pinned_empty() (inputs, out=, ok_out=) no staging copy is made: the kernels read and write them in place."""
         w, dt, f = self._out_fmt(output)
         f |= (0 if zip216 else L.JJ_PRE_ZIP216) | (L.JJ_CHECK_SUBGROUP if check_subgroup else 0) | flags
         return self._call("jj_scalar_mul_encoded", [(encodings, 32, np.uint8), (scalars, 32, np.uint8)], w, dt,
-                          flags=f, ok=True)
+                          flags=f, ok=True, out=out, ok_out=ok_out)
 
     def scalar_mul_fixed_vartime(self, base_affine, scalars, output="extended", scalar_mont=False, out=None):
         """out[i] = [scalars[i]] base  (`&AffinePoint * &Fr`, src/lib.rs:1109-1115), one shared base; variable-time."""

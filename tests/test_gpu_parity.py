@@ -634,6 +634,15 @@ def test_scalar_mul_encoded_pinned_buffers(eng, oracle):
         want, wok = eng.scalar_mul_encoded_vartime(enc[:m], k[:m])
         eng._check(eng.lib.jj_scalar_mul_encoded(eng.ctx, mis.ctypes.data, hk.ctypes.data, hout.ctypes.data, hok.ctypes.data, m, jj.JJ_OUT_BYTES))
         assert (hok[:m] == wok).all() and (hout.reshape(-1)[: m * 32].reshape(m, 32)[wok == 1] == want[wok == 1]).all()
+        # the same through the host mirror: Engine.pinned_empty() arrays as inputs, out= and ok_out=
+        m = 200000
+        pe, pk = eng.pinned_empty((m, 32), np.uint8), eng.pinned_empty((m, 32), np.uint8)
+        po, pok = eng.pinned_empty((m, 32), np.uint8), eng.pinned_empty((m,), np.uint8)
+        pe[:], pk[:] = enc[:m], k[:m]
+        want, wok = eng.scalar_mul_encoded_vartime(enc[:m], k[:m])
+        got, gok = eng.scalar_mul_encoded_vartime(pe, pk, out=po, ok_out=pok)
+        assert got is po and (gok == wok).all() and (pok == wok).all() and (po[wok == 1] == want[wok == 1]).all()
+        del pe, pk, po, pok, got, gok
     finally:
         for p in (p1, p2, p3, p4):
             eng.lib.jj_host_free(eng.ctx, p)
