@@ -1465,15 +1465,17 @@ int32_t jj_scalar_mul_sharded_n(jj_ctx* c, const void* points_local, const void*
             const size_t cnt = std::min(chunk, n_local - done);
             Staging& S = c->st[stage];
             CU(c, cudaStreamSynchronize(S.stream));
-            if (used < kStages) {
-                CU(c, cudaStreamWaitEvent(S.stream, c->ev_fork, 0));
-                used++;
-            }
             int32_t rc = ensure(c, &S.buf[0], &S.cap[0], chunk * 160, false);
             if (!rc) rc = ensure(c, &S.buf[1], &S.cap[1], chunk * 32, false);
             if (rc) return rc;
             CU(c, cudaMemcpyAsync(S.buf[0], (const char*)points_local + done * 160, cnt * 160, cudaMemcpyHostToDevice, S.stream));
             CU(c, cudaMemcpyAsync(S.buf[1], (const char*)scalars_local + done * 32, cnt * 32, cudaMemcpyHostToDevice, S.stream));
+            if (used < kStages) {
+                // the uploads above touch this rank's staging buffers only: they need not wait for the leading rendezvous
+                // (a rank that arrives early uploads its first chunks while it waits for the others); the kernels do
+                CU(c, cudaStreamWaitEvent(S.stream, c->ev_fork, 0));
+                used++;
+            }
             PeerOut pc = po;
             pc.base_unit = lo + done;
             rc = smul_any(c, S.stream, &S, S.buf[0], false, S.buf[1], fused ? nullptr : mine + done * unit, cnt, flags,
