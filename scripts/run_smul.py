@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--logn", type=int, default=17)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--what", default="smul", choices=["smul", "fixed", "fqmul", "torsion"])
+    ap.add_argument("--what", default="smul", choices=["smul", "fixed", "fqmul", "torsion", "decode"])
     ap.add_argument("--ct", action="store_true", help="constant-time mode (JJ_CONST_TIME)")
     a = ap.parse_args()
     eng = jj.Engine(0)
@@ -41,6 +41,13 @@ def main():
             eng.scalar_mul_fixed_vartime(generator(eng), k)
         return
     pts = eng.scalar_mul_fixed_vartime(generator(eng), t)
+    if a.what == "decode":
+        enc = eng.affine_to_bytes(eng.batch_normalize(pts))
+        for _ in range(a.reps):
+            eng.timer_start()
+            eng.batch_from_bytes(enc)
+            print(f"batch_from_bytes n={n}: {eng.timer_stop():.3f} ms")
+        return
     if a.what == "torsion":
         for _ in range(a.reps):
             eng.timer_start()
