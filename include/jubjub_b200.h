@@ -216,7 +216,8 @@ int32_t jj_affine_to_extended(jj_ctx* ctx, const void* p_affine, void* out_ext, 
 /* ExtendedPoint::mul_by_cofactor src/lib.rs:722-724 (= double().double().double(), all 160 B bit-exact) */
 int32_t jj_mul_by_cofactor(jj_ctx* ctx, const void* p_ext, void* out_ext, size_t n, uint32_t flags);
 /* ExtendedPoint::batch_normalize src/lib.rs:840-858: ExtendedPoint -> AffinePoint (z = 0 gives (0, 0)
- * like ff::BatchInverter's skipped zeros) */
+ * like ff::BatchInverter's skipped zeros).  With JJ_OUT_BYTES the same pass also encodes: out is n x 32 B,
+ * GroupEncoding::to_bytes for ExtendedPoint (`AffinePoint::from(self).to_bytes()`, src/lib.rs:1419-1421). */
 int32_t jj_batch_normalize(jj_ctx* ctx, const void* in_ext, void* out_affine, size_t n, uint32_t flags);
 /* The free function batch_normalize src/lib.rs:1084-1107: normalises the ExtendedPoints themselves,
  * (u, v, z, t1, t2) -> (u/z, v/z, 1, u/z, v/z) ((0, 0, 1, 0, 0) for z = 0); out_ext may be in_ext (in place, as the

@@ -1259,11 +1259,15 @@ int32_t jj_scalar_mul_fixed(jj_ctx* c, const void* base_affine, const void* scal
 int32_t jj_batch_normalize(jj_ctx* c, const void* in, void* out, size_t n, uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;
     if (in == out && n) return fail(c, JJ_ERR_INVALID_ARG, "batch_normalize output must not alias its input");
+    // JJ_OUT_BYTES: normalise and encode in one pass -- GroupEncoding::to_bytes for ExtendedPoint (src/lib.rs:1419-1421)
+    const int unit = (flags & JJ_OUT_BYTES) ? 32 : 64;
     In ins[3] = {{in, 160}, {nullptr, 0}, {nullptr, 0}};
-    Out outs[2] = {{out, 64}, {nullptr, 0}};
+    Out outs[2] = {{out, (size_t)unit}, {nullptr, 0}};
+    BatchOpts opts;
+    opts.direct_out0 = unit == 32;  // 32-byte results are stored into a page-locked caller buffer in place
     return run_batch(c, flags, n, ins, outs, [=](cudaStream_t s, const char** din, char** dout, size_t cnt, Staging* S) {
-        return normalize_launch(c, s, din[0], dout[0], cnt, 64, nullptr, nullptr, !S);
-    });
+        return normalize_launch(c, s, din[0], dout[0], cnt, unit, S ? &S->tmp2 : &c->tmp2, S ? &S->tmp2_cap : &c->tmp2_cap, !S);
+    }, opts);
 }
 int32_t jj_batch_normalize_extended(jj_ctx* c, const void* in, void* out, size_t n, uint32_t flags) {
     if (!c) return JJ_ERR_INVALID_ARG;

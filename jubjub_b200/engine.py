@@ -273,6 +273,10 @@ class Engine:
         """ExtendedPoint::batch_normalize (src/lib.rs:840-858): ExtendedPoint -> AffinePoint."""
         return self._call("jj_batch_normalize", [(p, EXT_W, np.uint64)], AFF_W, out=out)
 
+    def batch_normalize_to_bytes(self, p, out=None):
+        """GroupEncoding::to_bytes for ExtendedPoint (src/lib.rs:1419-1421): normalise + encode in one pass."""
+        return self._call("jj_batch_normalize", [(p, EXT_W, np.uint64)], 32, np.uint8, flags=L.JJ_OUT_BYTES, out=out)
+
     def batch_normalize_extended(self, p, in_place=False):
         """batch_normalize (src/lib.rs:1084-1107): the points themselves become (u/z, v/z, 1, u/z, v/z); in_place
         overwrites `p` like the reference's `&mut [ExtendedPoint]`."""

@@ -327,6 +327,31 @@ class ExtendedPoint:
     def identity(cls, n=1, engine=None):
         return cls.from_affine(AffinePoint.identity(n, engine))
 
+    @classmethod
+    def generator(cls, n=1, engine=None):
+        """The full-order generator (src/lib.rs:1380-1396) as an ExtendedPoint."""
+        return cls.from_affine(AffinePoint.generator(n, engine))
+
+    @classmethod
+    def from_bytes(cls, b, engine=None):
+        """GroupEncoding for ExtendedPoint (src/lib.rs:1407-1422): -> (points, is_some)."""
+        a, ok = AffinePoint.batch_from_bytes(b, engine)
+        return cls.from_affine(a), ok
+
+    from_bytes_unchecked = from_bytes  # the curve check cannot be skipped when parsing an encoding (:1414-1417)
+
+    def to_bytes(self):
+        """`AffinePoint::from(self).to_bytes()` (src/lib.rs:1419-1421): normalise + encode in one pass on the device."""
+        return self.eng.batch_normalize_to_bytes(self.data)
+
+    def clear_cofactor(self):
+        """CofactorGroup::clear_cofactor (src/lib.rs:1343-1345): [8]P as a SubgroupPoint."""
+        return SubgroupPoint(self.mul_by_cofactor())
+
+    def into_subgroup(self):
+        """CofactorGroup::into_subgroup (src/lib.rs:1347-1349): -> (SubgroupPoint, is_some = is_torsion_free)."""
+        return SubgroupPoint(self), self.is_torsion_free()
+
     def _same(self, o):
         if len(o) != len(self):
             raise ValueError(f"length mismatch: {len(self)} != {len(o)}")  # assert_eq!, src/lib.rs:841
@@ -347,6 +372,8 @@ class ExtendedPoint:
             return ExtendedPoint(self.eng.point_add_affine_niels(self.data, o.data, subtract=subtract), self.eng)
         if isinstance(o, AffinePoint):  # src/lib.rs:1012-1028
             return self._addsub(o.to_niels(), subtract)
+        if isinstance(o, SubgroupPoint):  # &ExtendedPoint +- &SubgroupPoint -> ExtendedPoint, src/lib.rs:1191-1209
+            return self._addsub(o.p, subtract)
         return NotImplemented
 
     def __add__(self, o):
@@ -417,6 +444,91 @@ class ExtendedPoint:
         return ExtendedPoint(self.data[i].reshape(-1, 20), self.eng)
 
 
+class SubgroupPoint:
+    """A batch of elements of the prime-order subgroup (src/lib.rs:1122: `SubgroupPoint(ExtendedPoint)`).  Like the
+    reference type it can only be built by routes that guarantee membership -- `ExtendedPoint.clear_cofactor()`,
+    `into_subgroup()` / `from_bytes()` (which report `is_torsion_free` per element), sums, negations, doublings and
+    scalar multiples of subgroup points -- or by the explicitly unchecked constructors."""
+
+    def __init__(self, p):
+        assert isinstance(p, ExtendedPoint)
+        self.p = p
+        self.eng = p.eng
+
+    def __len__(self):
+        return len(self.p)
+
+    @classmethod
+    def from_raw_unchecked(cls, u, v):
+        """src/lib.rs:1148-1158: the caller vouches for membership."""
+        return cls(AffinePoint.from_raw_unchecked(u, v).to_extended())
+
+    @classmethod
+    def identity(cls, n=1, engine=None):
+        return cls(ExtendedPoint.identity(n, engine))
+
+    @classmethod
+    def generator(cls, n=1, engine=None):
+        """`ExtendedPoint::generator().clear_cofactor()` (src/lib.rs:1304-1306)."""
+        return ExtendedPoint.generator(n, engine).clear_cofactor()
+
+    @classmethod
+    def from_bytes(cls, b, engine=None):
+        """GroupEncoding for SubgroupPoint (src/lib.rs:1427-1429): decoded AND torsion free -> (points, is_some).  The
+        subgroup test runs on the device (a pairing, not `[r]P`); rejected elements are the identity."""
+        p, ok = ExtendedPoint.from_bytes(b, engine)
+        ok = ok.astype(bool) & p.is_torsion_free().astype(bool)
+        data = p.data.copy()
+        data[~ok] = ExtendedPoint.identity(1, p.eng).data[0]
+        return cls(ExtendedPoint(data, p.eng)), ok.astype(np.uint8)
+
+    @classmethod
+    def from_bytes_unchecked(cls, b, engine=None):
+        """src/lib.rs:1431-1433: curve check only."""
+        p, ok = ExtendedPoint.from_bytes(b, engine)
+        return cls(p), ok
+
+    def to_bytes(self):
+        return self.p.to_bytes()
+
+    def to_extended(self):
+        """From<SubgroupPoint> for ExtendedPoint (src/lib.rs:1124-1128)."""
+        return self.p
+
+    def __add__(self, o):  # src/lib.rs:1211-1229
+        return SubgroupPoint(self.p + o.p) if isinstance(o, SubgroupPoint) else NotImplemented
+
+    def __sub__(self, o):
+        return SubgroupPoint(self.p - o.p) if isinstance(o, SubgroupPoint) else NotImplemented
+
+    def __neg__(self):  # src/lib.rs:1173-1189
+        return SubgroupPoint(-self.p)
+
+    def double(self):  # src/lib.rs:1312-1315
+        return SubgroupPoint(self.p.double())
+
+    def __mul__(self, k):  # src/lib.rs:1231-1239
+        r = self.p * k
+        return r if r is NotImplemented else SubgroupPoint(r)
+
+    def mul_vartime(self, k):
+        return SubgroupPoint(self.p.mul_vartime(k))
+
+    def sum(self):  # Sum<SubgroupPoint>, src/lib.rs:1161-1171
+        return SubgroupPoint(self.p.sum())
+
+    def is_identity(self):
+        return self.p.is_identity()
+
+    def __eq__(self, o):
+        return isinstance(o, SubgroupPoint) and self.p == o.p
+
+    __hash__ = None
+
+    def __getitem__(self, i):
+        return SubgroupPoint(self.p[i])
+
+
 # ---- free functions ---------------------------------------------------------------------------------
 def batch_normalize(points):
     """jubjub::batch_normalize (src/lib.rs:1084-1107): normalises the ExtendedPoint batch IN PLACE (z = 1, t1 = u,
@@ -435,5 +547,5 @@ def batch_add(p, q):
     return p + q
 
 
-__all__ = ["Fq", "Fr", "AffinePoint", "ExtendedPoint", "AffineNielsPoint", "ExtendedNielsPoint", "batch_normalize",
+__all__ = ["Fq", "Fr", "AffinePoint", "ExtendedPoint", "SubgroupPoint", "AffineNielsPoint", "ExtendedNielsPoint", "batch_normalize",
            "batch_mul_vartime", "batch_add", "acknowledge_vartime"]

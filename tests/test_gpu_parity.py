@@ -363,6 +363,15 @@ def test_batch_normalize_and_flags(eng, oracle):
     got = eng.batch_normalize(q)
     assert (got == want).all() and (got[5] == 0).all()
     assert (eng.affine_to_bytes(got) == oracle.affine_to_bytes(want)).all()
+    # GroupEncoding::to_bytes for ExtendedPoint (src/lib.rs:1419-1421): normalise + encode in one pass (JJ_OUT_BYTES),
+    # host buffers (pageable and page-locked: stored in place) and device resident
+    wenc = oracle.affine_to_bytes(want)
+    assert (eng.batch_normalize_to_bytes(q) == wenc).all()
+    assert (eng.batch_normalize_to_bytes(eng.to_device(q)).download() == wenc).all()
+    pin = eng.pinned_empty((len(q), 32), np.uint8)
+    pin[:] = 0xA5
+    assert eng.batch_normalize_to_bytes(q, out=pin) is pin and (pin == wenc).all()
+    del pin
     # src/lib.rs:1530-1575: p, 2p, 4p, ... normalised in a batch == one inversion each
     pt = oracle.ext_mul_by_cofactor(oracle.affine_to_extended(affine_raw(oracle, [K.TEST_POINT_RAW])))
     v = []

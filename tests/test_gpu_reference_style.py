@@ -135,6 +135,47 @@ def test_zip_216(T):  # src/lib.rs:1893-1935
         assert (encoded == b).all()
 
 
+def test_subgroup_point_surface(T, oracle):  # SubgroupPoint / CofactorGroup / GroupEncoding, src/lib.rs:1122-1239, 1287-1354, 1407-1434
+    n = 64
+    g = T.ExtendedPoint.generator(n)
+    k = T.Fr.from_u64(list(range(1, n + 1)))
+    full = g * k                                   # [k]G, G of order 8r: torsion free iff 8 | k
+    sub, ok = full.into_subgroup()                 # CtOption(SubgroupPoint(self), is_torsion_free)
+    assert isinstance(sub, T.SubgroupPoint) and sub.to_extended() == full
+    assert (ok.astype(bool) == (np.arange(1, n + 1) % 8 == 0)).all()
+    assert (full.is_torsion_free() == oracle.is_torsion_free(full.data)).all()
+    cleared = full.clear_cofactor()                # SubgroupPoint([8]P)
+    assert cleared.to_extended().is_torsion_free().all() and cleared.to_extended() == full.mul_by_cofactor()
+    sg = T.SubgroupPoint.generator(n)              # ExtendedPoint::generator().clear_cofactor()
+    assert sg.to_extended() == g.mul_by_cofactor() and not sg.is_identity().any()
+    assert (sg * k).to_extended() == cleared.to_extended()          # Mul<&Fr> for &SubgroupPoint
+    assert (sg * k).mul_vartime(T.Fr.one(n)) == sg * k
+    assert (sg + sg) == sg.double() and (sg - sg).is_identity().all() and (-sg + sg).is_identity().all()
+    assert (full + sg) == (full + sg.to_extended()) and (full - sg) == (full - sg.to_extended())  # ExtendedPoint +- SubgroupPoint
+    assert T.SubgroupPoint.identity(3).is_identity().all()
+    # Sum<SubgroupPoint>: sum_{k=1..n} [k] G8 = [n (n + 1) / 2] G8
+    tot = (sg * k).sum()
+    assert tot == T.SubgroupPoint.generator(1) * T.Fr.from_u64([n * (n + 1) // 2])
+    # GroupEncoding: to_bytes == the affine encoding; from_bytes = decode AND torsion free; from_bytes_unchecked = decode only
+    enc = full.to_bytes()
+    assert (enc == full.to_affine().to_bytes()).all()
+    assert (enc == oracle.affine_to_bytes(oracle.batch_normalize(full.data))).all()
+    back, ok1 = T.ExtendedPoint.from_bytes(enc)
+    assert ok1.all() and back == full
+    sp, ok2 = T.SubgroupPoint.from_bytes(enc)
+    assert (ok2.astype(bool) == (np.arange(1, n + 1) % 8 == 0)).all()
+    assert sp.to_extended().is_identity()[ok2 == 0].all()  # rejected elements are the identity
+    assert T.ExtendedPoint(sp.to_extended().data[ok2 == 1]) == T.ExtendedPoint(full.data[ok2 == 1])
+    su, ok3 = T.SubgroupPoint.from_bytes_unchecked(enc)
+    assert ok3.all() and su.to_extended() == full
+    bad = enc.copy()
+    bad[0] = 0xFF
+    assert T.SubgroupPoint.from_bytes(bad)[1][0] == 0 and T.ExtendedPoint.from_bytes(bad)[1][0] == 0
+    # from_raw_unchecked (src/lib.rs:1148-1158)
+    a8 = cleared.to_extended().to_affine()
+    assert T.SubgroupPoint.from_raw_unchecked(a8.get_u(), a8.get_v()) == cleared
+
+
 def test_field_surface(T):  # src/fr.rs:1045-1175 through the operator surface
     big = T.Fr(np.array([K.FR_LARGEST], dtype=np.uint64))
     assert big + big == T.Fr(np.array([K.FR_LARGEST_PLUS_LARGEST], dtype=np.uint64))
