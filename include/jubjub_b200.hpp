@@ -121,6 +121,12 @@ class Engine {
         check(jj_batch_normalize(ctx_, p.data(), out.data(), p.size(), 0));
         return out;
     }
+    // GroupEncoding::to_bytes for ExtendedPoint (src/lib.rs:1419-1421): normalise + encode in one pass
+    std::vector<std::array<uint8_t, 32>> batch_to_bytes(const std::vector<ExtendedPoint>& p) {
+        std::vector<std::array<uint8_t, 32>> out(p.size());
+        check(jj_batch_normalize(ctx_, p.data(), out.data(), p.size(), JJ_OUT_BYTES));
+        return out;
+    }
     // AffinePoint::to_bytes (src/lib.rs:455-464)
     std::vector<std::array<uint8_t, 32>> batch_to_bytes(const std::vector<AffinePoint>& p) {
         std::vector<std::array<uint8_t, 32>> out(p.size());

@@ -63,6 +63,11 @@ int main(int argc, char** argv) {
             auto again = eng.batch_normalize(eng.batch_sum(halves));
             if (std::memcmp(whole.data(), again.data(), sizeof(AffinePoint)) != 0) return 13;
         }
+        // ExtendedPoint::to_bytes (src/lib.rs:1419-1421) == AffinePoint::from(p).to_bytes()
+        auto e1 = eng.batch_to_bytes(p);
+        auto e2 = eng.batch_to_bytes(a0);
+        for (uint64_t i = 0; i < n; i++)
+            if (std::memcmp(e1[i].data(), e2[i].data(), 32) != 0) return 16;
         // Neg / PartialEq / From<AffinePoint> (src/lib.rs:153-226): p == from_affine(normalize(p)), -(-p) == p bit for bit,
         // p + (-p) == identity == its own negation
         auto back = eng.batch_from_affine(a0);
