@@ -92,8 +92,14 @@ class Engine:
         self._check(self.lib.jj_host_alloc(self.ctx, nbytes, C.byref(p)))
         buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        lib, ctx, addr = self.lib, self.ctx, p.value
-        weakref.finalize(buf, lambda: lib.jj_host_free(ctx, C.c_void_p(addr)) if ctx else None)
+        eng_ref, addr = weakref.ref(self), p.value
+
+        def _free():  # only through a context that is still alive (a closed engine's pinned buffers are left to the driver)
+            e = eng_ref()
+            if e is not None and e.ctx:
+                e.lib.jj_host_free(e.ctx, C.c_void_p(addr))
+
+        weakref.finalize(buf, _free)
         return arr
 
     def to_device(self, host):
